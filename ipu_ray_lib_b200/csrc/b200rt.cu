@@ -1,0 +1,582 @@
+// b200rt.cu — the C ABI of include/b200rt.h over the sm_100a kernels in trace_kernels.cuh.
+//
+// One b200rt_scene == one replica of the reference's IpuScene (src/IpuScene.cpp): the scene arrays
+// are uploaded once (the reference broadcasts them to every tile, :477-483), the TraceResult stream
+// is copied to HBM, rendered in place and copied back. There is no CPU fallback anywhere in this
+// file: without an sm_100 device every compute entry point returns B200RT_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200rt.h"
+#include "nif.cuh"
+#include "trace_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(e__ == cudaErrorMemoryAllocation ? B200RT_ERR_OOM : B200RT_ERR_CUDA,            \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                           \
+  } while (0)
+
+struct DeviceBuffer {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t upload(const void* src, size_t n, size_t padTo = 16) {
+    bytes = ((n + padTo - 1) / padTo) * padTo;
+    if (bytes == 0) bytes = padTo;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpy(p, src, n, cudaMemcpyHostToDevice);
+    return e;
+  }
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+// Host mirrors of the reference records (layouts asserted in host/rt_types.hpp).
+struct GeomRefH { uint16_t index; uint8_t type; uint8_t pad; };
+struct MeshInfoH { uint32_t firstIndex, firstVertex, numTriangles, numVertices; };
+
+}  // namespace
+
+struct b200rt_scene {
+  int device = 0;
+  int numSMs = 0;
+  int maxSmemOptin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t evStart = nullptr, evStop = nullptr;
+  b200rt_scene_desc desc{};  // scalars only are used after creation
+  rt::DevScene dev{};
+  uint32_t nodeBytes = 0;
+  DeviceBuffer nodes, geoms, triVerts, triNormals, spheres, discs, matIDs, materials;
+  DeviceBuffer workCounter, counters;
+  DeviceBuffer rays;                                   // device copy of the stream (host-buffer entry point)
+  DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
+  b200rt_trace_stats stats{};
+  float hdriRotationDegrees = 0.f;
+  size_t maxNifBatch = 0;
+  rt::NifModel* nif = nullptr;
+
+  ~b200rt_scene() {
+    cudaSetDevice(device);
+    if (nif) rt::nif_destroy(nif);
+    for (DeviceBuffer* b : {&nodes, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
+                            &workCounter, &counters, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
+                            &escapeCount})
+      b->release();
+    if (evStart) cudaEventDestroy(evStart);
+    if (evStop) cudaEventDestroy(evStop);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int validate_desc(const b200rt_scene_desc& d) {
+  if (d.num_bvh_nodes == 0 || !d.bvh_nodes) return fail(B200RT_ERR_INVALID_ARG, "scene has no BVH nodes");
+  if (d.num_geometry == 0 || !d.geometry) return fail(B200RT_ERR_INVALID_ARG, "scene has no geometry");
+  if (d.num_mat_ids < d.num_geometry || !d.mat_ids)
+    return fail(B200RT_ERR_INVALID_ARG, "All primitives must be assigned a material.");
+  if (d.num_materials == 0 || !d.materials) return fail(B200RT_ERR_INVALID_ARG, "scene has no materials");
+  if (d.num_normals != 0 && d.num_normals != d.num_verts)
+    return fail(B200RT_ERR_INVALID_ARG, "mesh_normals must be empty or one per vertex");
+  if (d.max_leaf_depth > (uint32_t)rt::kMaxStack)
+    return fail(B200RT_ERR_UNSUPPORTED, "BVH deeper than 64 levels");
+  const auto* mat = (const uint32_t*)d.mat_ids;
+  for (uint32_t i = 0; i < d.num_geometry; ++i)
+    if (mat[i] >= d.num_materials) return fail(B200RT_ERR_INVALID_ARG, "material index out of range");
+  return B200RT_OK;
+}
+
+template <bool kShared, bool kOrdered, bool kCount>
+cudaError_t launch_shadow(const rt::TraceArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+  auto k = rt::shadow_trace_kernel<kShared, kOrdered, kCount>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<grid, block, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <bool kShared, bool kOrdered, bool kCount, bool kNif>
+cudaError_t launch_path(const rt::TraceArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+  auto k = rt::path_trace_kernel<kShared, kOrdered, kCount, kNif>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<grid, block, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <bool kShared, bool kOrdered>
+cudaError_t dispatch_shadow(bool count, const rt::TraceArgs& a, int g, int b, size_t s, cudaStream_t st) {
+  return count ? launch_shadow<kShared, kOrdered, true>(a, g, b, s, st)
+               : launch_shadow<kShared, kOrdered, false>(a, g, b, s, st);
+}
+template <bool kShared, bool kOrdered>
+cudaError_t dispatch_path(bool count, bool nif, const rt::TraceArgs& a, int g, int b, size_t s, cudaStream_t st) {
+  if (count) return nif ? launch_path<kShared, kOrdered, true, true>(a, g, b, s, st)
+                        : launch_path<kShared, kOrdered, true, false>(a, g, b, s, st);
+  return nif ? launch_path<kShared, kOrdered, false, true>(a, g, b, s, st)
+             : launch_path<kShared, kOrdered, false, false>(a, g, b, s, st);
+}
+
+struct LaunchPlan {
+  bool shared, ordered, count;
+  int grid, block;
+  size_t smem;
+};
+
+LaunchPlan plan_launch(const b200rt_scene& sc, const b200rt_trace_params& p) {
+  LaunchPlan L;
+  L.ordered = p.traversal != 1;  // auto = near-first
+  const size_t need = ((size_t)sc.nodeBytes + 15) / 16 * 16;
+  const bool fits = need + 1024 <= (size_t)sc.maxSmemOptin;
+  L.shared = p.scene_residency == 1 ? fits : (p.scene_residency == 2 ? false : fits);
+  L.count = p.count_visits != 0;
+  if (L.shared) {
+    L.block = 512;  // one CTA per SM owns the staged BVH; 16 warps hide the shared-memory latency
+    L.grid = sc.numSMs;
+    L.smem = need;
+  } else {
+    L.block = 128;
+    L.grid = sc.numSMs * 4;
+    L.smem = 0;
+  }
+  return L;
+}
+
+cudaError_t run_shadow(b200rt_scene& sc, const LaunchPlan& L, const rt::TraceArgs& a) {
+  if (L.shared) return L.ordered ? dispatch_shadow<true, true>(L.count, a, L.grid, L.block, L.smem, sc.stream)
+                                 : dispatch_shadow<true, false>(L.count, a, L.grid, L.block, L.smem, sc.stream);
+  return L.ordered ? dispatch_shadow<false, true>(L.count, a, L.grid, L.block, L.smem, sc.stream)
+                   : dispatch_shadow<false, false>(L.count, a, L.grid, L.block, L.smem, sc.stream);
+}
+cudaError_t run_path(b200rt_scene& sc, const LaunchPlan& L, bool nif, const rt::TraceArgs& a) {
+  if (L.shared) return L.ordered ? dispatch_path<true, true>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream)
+                                 : dispatch_path<true, false>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream);
+  return L.ordered ? dispatch_path<false, true>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream)
+                   : dispatch_path<false, false>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream);
+}
+
+float host_tan_half_fov(float fov) {
+  float s, c;
+  rt::sincos_tbl(fov / 2.f, s, c);
+  return s / c;
+}
+
+// Renders d_rays[0..n) in place on sc.stream. Adds to sc.stats (kernel time via events).
+int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, size_t n, cudaStream_t stream) {
+  if (n == 0) return B200RT_OK;
+  if (n > 0xFFFFFFFFull) return fail(B200RT_ERR_INVALID_ARG, "ray stream longer than 2^32 rays");
+  cudaStream_t saved = sc.stream;
+  if (stream) sc.stream = stream;
+  struct Restore { b200rt_scene& s; cudaStream_t v; ~Restore() { s.stream = v; } } restore{sc, saved};
+
+  const LaunchPlan L = plan_launch(sc, p);
+  rt::TraceArgs a{};
+  a.scene = sc.dev;
+  a.rays = d_rays;
+  a.numRays = (uint32_t)n;
+  a.workCounter = (uint32_t*)sc.workCounter.p;
+  a.counters = (rt::DeviceCounters*)sc.counters.p;
+  a.nodeBytes = sc.nodeBytes;
+  CU_TRY(cudaMemsetAsync(sc.counters.p, 0, sizeof(rt::DeviceCounters), sc.stream));
+  CU_TRY(cudaEventRecord(sc.evStart, sc.stream));
+  uint64_t launches = 0;
+
+  if (!sc.desc.path_trace) {
+    const bool dflt = p.light_pos[0] == 0.f && p.light_pos[1] == 0.f && p.light_pos[2] == 0.f && p.ambient == 0.f;
+    a.lightX = dflt ? 18.f : p.light_pos[0];
+    a.lightY = dflt ? 257.f : p.light_pos[1];
+    a.lightZ = dflt ? -1060.f : p.light_pos[2];
+    a.ambient = dflt ? .05f : p.ambient;
+    CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
+    CU_TRY(run_shadow(sc, L, a));
+    launches += 1;
+  } else {
+    if (!(sc.desc.image_width >= 1.f) || !(sc.desc.image_height >= 1.f))
+      return fail(B200RT_ERR_INVALID_ARG, "image_width/image_height must be set for path tracing");
+    a.imageWidth = sc.desc.image_width;
+    a.imageHeight = sc.desc.image_height;
+    a.tanTheta = host_tan_half_fov(sc.desc.fov_radians);
+    a.antiAlias = sc.desc.anti_alias_scale;
+    a.maxPathLength = sc.desc.max_path_length;
+    a.rouletteStartDepth = sc.desc.roulette_start_depth;
+    a.rngKey = rt::splitmix64(sc.desc.rng_seed);
+    const uint32_t first = p.first_sample;
+    const uint32_t count = p.num_samples ? p.num_samples : sc.desc.samples_per_pixel;
+    if (!sc.nif) {
+      a.firstSample = first;
+      a.endSample = first + count;
+      CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
+      CU_TRY(run_path(sc, L, false, a));
+      launches += 1;
+    } else {
+      // Wavefront over chunks of samples: trace -> (compacted escaped rays) NIF -> ordered accumulate.
+      uint32_t chunk = p.samples_per_chunk ? p.samples_per_chunk : 32u;
+      // bound the slot arrays to ~8 GiB
+      const size_t perSlot = (3 + 5 + 3 + 1) * sizeof(float);
+      while (chunk > 1 && (size_t)chunk * n * perSlot > (size_t)8 << 30) chunk /= 2;
+      if (chunk > count) chunk = count ? count : 1;
+      CU_TRY(sc.slotColor.reserve((size_t)chunk * n * 3 * sizeof(float)));
+      CU_TRY(sc.slotEscape.reserve((size_t)chunk * n * 5 * sizeof(float)));
+      CU_TRY(sc.slotEnv.reserve((size_t)chunk * n * 3 * sizeof(float)));
+      CU_TRY(sc.escapeQueue.reserve((size_t)chunk * n * sizeof(uint32_t)));
+      CU_TRY(sc.escapeCount.reserve(16));
+      a.slotColor = (float*)sc.slotColor.p;
+      a.slotEscape = (float*)sc.slotEscape.p;
+      a.escapeQueue = (uint32_t*)sc.escapeQueue.p;
+      a.escapeCount = (uint32_t*)sc.escapeCount.p;
+      a.hdriRotation = (sc.hdriRotationDegrees / 360.f) * (float)(2.0 * M_PI);  // src/IpuScene.cpp:641
+      for (uint32_t s0 = first; s0 < first + count; s0 += chunk) {
+        const uint32_t c = std::min(chunk, first + count - s0);
+        a.firstSample = s0;
+        a.endSample = s0 + c;
+        CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
+        CU_TRY(cudaMemsetAsync(sc.escapeCount.p, 0, 4, sc.stream));
+        CU_TRY(run_path(sc, L, true, a));
+        launches += 1;
+        int nifLaunches = 0;
+        const int rc = rt::nif_eval_queue(sc.nif, (const float*)sc.slotEscape.p, (const uint32_t*)sc.escapeQueue.p,
+                                          (const uint32_t*)sc.escapeCount.p, (uint32_t)std::min<size_t>((size_t)c * n, 0xFFFFFFFFull),
+                                          (float*)sc.slotEnv.p, sc.stream, &nifLaunches);
+        if (rc != 0) return fail(B200RT_ERR_CUDA, std::string("NIF evaluation failed: ") + rt::nif_last_error());
+        launches += (uint64_t)nifLaunches;
+        const uint32_t threads = 256, blocks = (uint32_t)((n + threads - 1) / threads);
+        rt::accumulate_kernel<<<blocks, threads, 0, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,
+                                                                 (const float*)sc.slotEscape.p, (const float*)sc.slotEnv.p);
+        CU_TRY(cudaGetLastError());
+        launches += 1;
+      }
+    }
+  }
+  CU_TRY(cudaEventRecord(sc.evStop, sc.stream));
+  CU_TRY(cudaStreamSynchronize(sc.stream));
+  float ms = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms, sc.evStart, sc.evStop));
+  rt::DeviceCounters hc{};
+  CU_TRY(cudaMemcpy(&hc, sc.counters.p, sizeof(hc), cudaMemcpyDeviceToHost));
+  sc.stats.closest_hit_queries += hc.closest;
+  sc.stats.occlusion_queries += hc.occlusion;
+  sc.stats.node_visits += hc.nodeVisits;
+  sc.stats.prim_tests += hc.primTests;
+  sc.stats.samples += hc.samples;
+  sc.stats.escaped_samples += hc.escaped;
+  sc.stats.kernel_ms += ms;
+  sc.stats.kernel_launches += launches;
+  return B200RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200rt_abi_version(void) { return B200RT_ABI_VERSION; }
+const char* b200rt_last_error(void) { return g_error.c_str(); }
+
+int b200rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int usable = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) usable++;
+  }
+  return usable;
+}
+
+int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
+  if (!d || !out) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (int rc = validate_desc(*d)) return rc;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(B200RT_ERR_CUDA, "no CUDA device: the trace path has no CPU fallback");
+  }
+  int device = d->device;
+  if (device < 0) CU_TRY(cudaGetDevice(&device));
+  if (device >= count) return fail(B200RT_ERR_INVALID_ARG, "device ordinal out of range");
+  int major = 0;
+  CU_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return fail(B200RT_ERR_UNSUPPORTED, "kernels are built for sm_100a (B200) only");
+  CU_TRY(cudaSetDevice(device));
+
+  b200rt_scene* sc = new (std::nothrow) b200rt_scene();
+  if (!sc) return fail(B200RT_ERR_OOM, "out of host memory");
+  struct Guard { b200rt_scene* s; ~Guard() { delete s; } } guard{sc};
+  sc->device = device;
+  sc->desc = *d;
+  CU_TRY(cudaDeviceGetAttribute(&sc->numSMs, cudaDevAttrMultiProcessorCount, device));
+  CU_TRY(cudaDeviceGetAttribute(&sc->maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  CU_TRY(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreate(&sc->evStart));
+  CU_TRY(cudaEventCreate(&sc->evStop));
+
+  // --- node array: uploaded unchanged ---
+  sc->nodeBytes = d->num_bvh_nodes * 24u;
+  CU_TRY(sc->nodes.upload(d->bvh_nodes, sc->nodeBytes));
+
+  // --- geomID -> (type, first) table and gathered triangle vertices ---
+  const auto* geom = (const GeomRefH*)d->geometry;
+  const auto* info = (const MeshInfoH*)d->mesh_info;
+  const auto* tris = (const uint16_t*)d->mesh_tris;
+  const auto* verts = (const float*)d->mesh_verts;
+  const auto* normals = (const float*)d->mesh_normals;
+  std::vector<rt::GeomEntry> geoms(d->num_geometry);
+  for (uint32_t g = 0; g < d->num_geometry; ++g) {
+    geoms[g].type = geom[g].type;
+    if (geom[g].type == 0) {
+      if (geom[g].index >= d->num_meshes) return fail(B200RT_ERR_INVALID_ARG, "GeomRef mesh index out of range");
+      geoms[g].first = info[geom[g].index].firstIndex;
+    } else if (geom[g].type == 1) {
+      if (geom[g].index >= d->num_spheres) return fail(B200RT_ERR_INVALID_ARG, "GeomRef sphere index out of range");
+      geoms[g].first = geom[g].index;
+    } else if (geom[g].type == 2) {
+      if (geom[g].index >= d->num_discs) return fail(B200RT_ERR_INVALID_ARG, "GeomRef disc index out of range");
+      geoms[g].first = geom[g].index;
+    } else {
+      return fail(B200RT_ERR_INVALID_ARG, "unknown GeomType");
+    }
+  }
+  std::vector<float> tv((size_t)d->num_tris * 12, 0.f), tn;
+  if (d->num_normals) tn.assign((size_t)d->num_tris * 12, 0.f);
+  for (uint32_t m = 0; m < d->num_meshes; ++m) {
+    const MeshInfoH& mi = info[m];
+    if ((uint64_t)mi.firstIndex + mi.numTriangles > d->num_tris || (uint64_t)mi.firstVertex + mi.numVertices > d->num_verts)
+      return fail(B200RT_ERR_INVALID_ARG, "MeshInfo range exceeds the unified arrays");
+    for (uint32_t t = 0; t < mi.numTriangles; ++t) {
+      const size_t gt = (size_t)mi.firstIndex + t;
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t vi = tris[3 * gt + k];
+        if (vi >= mi.numVertices) return fail(B200RT_ERR_INVALID_ARG, "triangle index exceeds its mesh's vertex window");
+        const size_t gv = (size_t)mi.firstVertex + vi;
+        std::memcpy(&tv[12 * gt + 4 * k], verts + 3 * gv, 12);
+        if (d->num_normals) std::memcpy(&tn[12 * gt + 4 * k], normals + 3 * gv, 12);
+      }
+    }
+  }
+  CU_TRY(sc->geoms.upload(geoms.data(), geoms.size() * sizeof(rt::GeomEntry)));
+  CU_TRY(sc->triVerts.upload(tv.data(), tv.size() * sizeof(float)));
+  if (d->num_normals) CU_TRY(sc->triNormals.upload(tn.data(), tn.size() * sizeof(float)));
+  CU_TRY(sc->spheres.upload(d->spheres, (size_t)d->num_spheres * 16));
+  CU_TRY(sc->discs.upload(d->discs, (size_t)d->num_discs * 28));
+  CU_TRY(sc->matIDs.upload(d->mat_ids, (size_t)d->num_mat_ids * 4));
+  CU_TRY(sc->materials.upload(d->materials, (size_t)d->num_materials * 36));
+  CU_TRY(sc->workCounter.upload(nullptr, 16));
+  CU_TRY(sc->counters.upload(nullptr, sizeof(rt::DeviceCounters)));
+
+  sc->dev.nodes = (const uint2*)sc->nodes.p;
+  sc->dev.geoms = (const rt::GeomEntry*)sc->geoms.p;
+  sc->dev.triVerts = (const float4*)sc->triVerts.p;
+  sc->dev.triNormals = d->num_normals ? (const float4*)sc->triNormals.p : nullptr;
+  sc->dev.spheres = (const float4*)sc->spheres.p;
+  sc->dev.discs = (const float*)sc->discs.p;
+  sc->dev.matIDs = (const uint32_t*)sc->matIDs.p;
+  sc->dev.materials = (const float*)sc->materials.p;
+  sc->dev.numNodes = d->num_bvh_nodes;
+  sc->dev.numMaterials = d->num_materials;
+  // the scalars stay; the host pointers must not be used after creation
+  sc->desc.geometry = sc->desc.mesh_info = sc->desc.mesh_tris = sc->desc.mesh_verts = sc->desc.mesh_normals = nullptr;
+  sc->desc.mat_ids = nullptr; sc->desc.materials = sc->desc.bvh_nodes = nullptr;
+  sc->desc.spheres = sc->desc.discs = nullptr;
+  guard.s = nullptr;
+  *out = sc;
+  return B200RT_OK;
+}
+
+void b200rt_scene_destroy(b200rt_scene* sc) { delete sc; }
+
+int b200rt_scene_load_nif(b200rt_scene* sc, const b200rt_nif_desc* nif) {
+  if (!sc || !nif) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  CU_TRY(cudaSetDevice(sc->device));
+  if (sc->nif) { rt::nif_destroy(sc->nif); sc->nif = nullptr; }
+  sc->nif = rt::nif_create(*nif, sc->device);
+  if (!sc->nif) return fail(B200RT_ERR_INVALID_ARG, std::string("could not load NIF model: ") + rt::nif_last_error());
+  return B200RT_OK;
+}
+
+int b200rt_scene_set_hdri_rotation(b200rt_scene* sc, float degrees) {
+  if (!sc) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  sc->hdriRotationDegrees = degrees;
+  return B200RT_OK;
+}
+
+int b200rt_scene_set_max_nif_batch_size(b200rt_scene* sc, size_t n) {
+  if (!sc) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  sc->maxNifBatch = n;
+  return B200RT_OK;
+}
+
+int b200rt_nif_eval(b200rt_scene* sc, const float* uv, size_t n, float* bgrOut) {
+  if (!sc || !uv || !bgrOut) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  if (!sc->nif) return fail(B200RT_ERR_INVALID_ARG, "no NIF model loaded");
+  CU_TRY(cudaSetDevice(sc->device));
+  if (n == 0) return B200RT_OK;
+  DeviceBuffer dUv, dOut;
+  struct Free { DeviceBuffer& a; DeviceBuffer& b; ~Free() { a.release(); b.release(); } } fr{dUv, dOut};
+  CU_TRY(dUv.upload(uv, n * 2 * sizeof(float)));
+  CU_TRY(dOut.reserve(n * 3 * sizeof(float)));
+  int launches = 0;
+  if (rt::nif_eval_uv(sc->nif, (const float*)dUv.p, (uint32_t)n, (float*)dOut.p, sc->stream, &launches) != 0)
+    return fail(B200RT_ERR_CUDA, std::string("NIF evaluation failed: ") + rt::nif_last_error());
+  CU_TRY(cudaStreamSynchronize(sc->stream));
+  CU_TRY(cudaMemcpy(bgrOut, dOut.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  sc->stats.kernel_launches += (uint64_t)launches;
+  return B200RT_OK;
+}
+
+int b200rt_trace_device(b200rt_scene* sc, const b200rt_trace_params* params, void* dRays, size_t n, void* stream) {
+  if (!sc || !dRays) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  CU_TRY(cudaSetDevice(sc->device));
+  b200rt_trace_params p{};
+  if (params) p = *params;
+  sc->stats = b200rt_trace_stats{};
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = render_device(*sc, p, (float*)dRays, n, (cudaStream_t)stream);
+  sc->stats.trace_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
+
+int b200rt_trace(b200rt_scene* sc, const b200rt_trace_params* params, void* rays, size_t n, b200rt_ray_cb cb,
+                 void* user) {
+  if (!sc || (!rays && n)) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  CU_TRY(cudaSetDevice(sc->device));
+  b200rt_trace_params p{};
+  if (params) p = *params;
+  sc->stats = b200rt_trace_stats{};
+  if (n == 0) return B200RT_OK;
+  const size_t bytes = n * 84;
+  CU_TRY(sc->rays.reserve(bytes));
+
+  // host -> HBM (the reference's copyToRemoteBuffer, src/IpuScene.cpp:676-684; untimed there, timed here)
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  struct Ev { cudaEvent_t a, b; ~Ev() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev{e0, e1};
+  CU_TRY(cudaEventRecord(e0, sc->stream));
+  CU_TRY(cudaMemcpyAsync(sc->rays.p, rays, bytes, cudaMemcpyHostToDevice, sc->stream));
+  CU_TRY(cudaEventRecord(e1, sc->stream));
+  CU_TRY(cudaStreamSynchronize(sc->stream));
+  float ms = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  sc->stats.h2d_ms = ms;
+
+  const auto t0 = std::chrono::steady_clock::now();
+  if (int rc = render_device(*sc, p, (float*)sc->rays.p, n, nullptr)) return rc;
+  sc->stats.trace_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  // HBM -> host, batch by batch so a callback sees the reference's batch granularity
+  // (rays per batch = raysPerWorker * 6 * 1440 per replica, src/IpuScene.cpp:78-108).
+  const size_t batch = p.rays_per_batch ? p.rays_per_batch : 8640;
+  CU_TRY(cudaEventRecord(e0, sc->stream));
+  if (!cb) {
+    CU_TRY(cudaMemcpyAsync(rays, sc->rays.p, bytes, cudaMemcpyDeviceToHost, sc->stream));
+    CU_TRY(cudaEventRecord(e1, sc->stream));
+    CU_TRY(cudaStreamSynchronize(sc->stream));
+  } else {
+    size_t index = 0;
+    for (size_t off = 0; off < n; off += batch, ++index) {
+      const size_t cnt = std::min(batch, n - off);
+      char* dst = (char*)rays + off * 84;
+      CU_TRY(cudaMemcpyAsync(dst, (char*)sc->rays.p + off * 84, cnt * 84, cudaMemcpyDeviceToHost, sc->stream));
+      CU_TRY(cudaStreamSynchronize(sc->stream));
+      cb(index, dst, cnt, user);
+    }
+    CU_TRY(cudaEventRecord(e1, sc->stream));
+    CU_TRY(cudaStreamSynchronize(sc->stream));
+  }
+  CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  sc->stats.d2h_ms = ms;
+  return B200RT_OK;
+}
+
+int b200rt_get_trace_stats(const b200rt_scene* sc, b200rt_trace_stats* out) {
+  if (!sc || !out) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  *out = sc->stats;
+  return B200RT_OK;
+}
+
+double b200rt_get_trace_time_secs(const b200rt_scene* sc) { return sc ? sc->stats.trace_secs : 0.0; }
+
+int b200rt_intersect(b200rt_scene* sc, const void* raysIn, size_t n, b200rt_hit* hitsOut, uint32_t traversal) {
+  if (!sc || !raysIn || !hitsOut) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  CU_TRY(cudaSetDevice(sc->device));
+  sc->stats = b200rt_trace_stats{};
+  if (n == 0) return B200RT_OK;
+  DeviceBuffer dR, dH;
+  struct Free { DeviceBuffer& a; DeviceBuffer& b; ~Free() { a.release(); b.release(); } } fr{dR, dH};
+  CU_TRY(dR.upload(raysIn, n * 32));
+  CU_TRY(dH.reserve(n * sizeof(rt::QueryHit)));
+  CU_TRY(cudaMemsetAsync(sc->counters.p, 0, sizeof(rt::DeviceCounters), sc->stream));
+  const uint32_t threads = 128, blocks = (uint32_t)((n + threads - 1) / threads);
+  if (traversal == 1)
+    rt::intersect_kernel<false><<<blocks, threads, 0, sc->stream>>>(sc->dev, (const float*)dR.p, (uint32_t)n,
+                                                                   (rt::QueryHit*)dH.p, (rt::DeviceCounters*)sc->counters.p);
+  else
+    rt::intersect_kernel<true><<<blocks, threads, 0, sc->stream>>>(sc->dev, (const float*)dR.p, (uint32_t)n,
+                                                                  (rt::QueryHit*)dH.p, (rt::DeviceCounters*)sc->counters.p);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(sc->stream));
+  static_assert(sizeof(rt::QueryHit) == sizeof(b200rt_hit), "hit record");
+  CU_TRY(cudaMemcpy(hitsOut, dH.p, n * sizeof(b200rt_hit), cudaMemcpyDeviceToHost));
+  rt::DeviceCounters hc{};
+  CU_TRY(cudaMemcpy(&hc, sc->counters.p, sizeof(hc), cudaMemcpyDeviceToHost));
+  sc->stats.closest_hit_queries = hc.closest;
+  sc->stats.node_visits = hc.nodeVisits;
+  sc->stats.prim_tests = hc.primTests;
+  sc->stats.kernel_launches = 1;
+  return B200RT_OK;
+}
+
+int b200rt_occluded(b200rt_scene* sc, const void* raysIn, size_t n, uint8_t* out) {
+  if (!sc || !raysIn || !out) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  CU_TRY(cudaSetDevice(sc->device));
+  if (n == 0) return B200RT_OK;
+  DeviceBuffer dR, dO;
+  struct Free { DeviceBuffer& a; DeviceBuffer& b; ~Free() { a.release(); b.release(); } } fr{dR, dO};
+  CU_TRY(dR.upload(raysIn, n * 32));
+  CU_TRY(dO.reserve(n));
+  const uint32_t threads = 128, blocks = (uint32_t)((n + threads - 1) / threads);
+  rt::occluded_kernel<<<blocks, threads, 0, sc->stream>>>(sc->dev, (const float*)dR.p, (uint32_t)n, (unsigned char*)dO.p);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(sc->stream));
+  CU_TRY(cudaMemcpy(out, dO.p, n, cudaMemcpyDeviceToHost));
+  return B200RT_OK;
+}
+
+}  // extern "C"

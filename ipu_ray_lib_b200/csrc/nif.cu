@@ -1,0 +1,228 @@
+// NIF (neural image field) environment light: (u,v) -> Fourier features -> dense ReLU MLP -> decode.
+//
+// What it computes (reference: the Poplar graph built by src/neural_networks/NifModel.cpp):
+//   encode  (:186-219, host twin :417-433)  un = 2*(u-1), vn = 2*(v-1); for j < E: a = fp16(un*2^j) ...
+//           features = [sin(un*2^j)]_E, [sin(vn*2^j)]_E, [cos(un*2^j)]_E, [cos(vn*2^j)]_E   (fp16)
+//   MLP     (:296-327)  x = act(x.W + b) per Dense layer, fp16 weights and fp16 layer outputs; where a
+//           layer's input width differs from the running width the encoded input is concatenated first
+//           (auto-detected skip connection, :303-309)
+//   decode  (:222-246)  fp32: exp(x*max + mean)   (mean already has -eps folded in, NifMetaData.cpp:48-53)
+// Numerics chosen for B200: products of fp16 operands accumulated in fp32 (the IPU used fp16
+// partials, src/IpuScene.cpp:256-262), one rounding to fp16 per layer output.
+//
+// This translation unit is compiled with FMA contraction enabled: nothing here is bit-compared with the
+// reference (it has no CPU NIF); parity is checked against oracle/oracle_port.cpp within a stated tolerance.
+#include "nif.cuh"
+
+#include <cuda_fp16.h>
+
+#include <string>
+#include <vector>
+
+namespace rt {
+
+namespace {
+thread_local std::string g_nifError;
+
+constexpr int kMaxLayers = 16;
+constexpr int kTileRows = 16;     // rows per CTA pass in the CUDA-core kernel
+constexpr int kThreads = 256;
+constexpr int kMaxWidth = 512;    // widest activation (incl. concatenated input) the smem tile holds
+
+struct LayerDev {
+  const __half* w;     // [in][out] row-major
+  const __half* b;     // [out] or nullptr
+  int in, out;
+  int relu;
+  int concat;          // 1: input of this layer = concat(previous activations, encoded features)
+};
+
+struct NifParams {
+  LayerDev layers[kMaxLayers];
+  int numLayers;
+  int embed;           // E; feature width = 4E
+  float maxv, mean0, mean1, mean2;
+  int logToneMap;
+};
+}  // namespace
+
+struct NifModel {
+  NifParams p{};
+  std::vector<void*> allocs;
+  int device = 0;
+};
+
+const char* nif_last_error() { return g_nifError.c_str(); }
+
+void nif_destroy(NifModel* m) {
+  if (!m) return;
+  for (void* a : m->allocs) cudaFree(a);
+  delete m;
+}
+
+NifModel* nif_create(const b200rt_nif_desc& d, int device) {
+  auto bad = [&](const std::string& s) -> NifModel* { g_nifError = s; return nullptr; };
+  if (d.num_layers == 0 || d.num_layers > (uint32_t)kMaxLayers || !d.layers) return bad("bad layer count");
+  if (d.embedding_dimension == 0 || d.embedding_dimension > 16) return bad("bad embedding dimension");
+  const int feat = 4 * (int)d.embedding_dimension;
+  NifModel* m = new NifModel();
+  m->device = device;
+  m->p.numLayers = (int)d.num_layers;
+  m->p.embed = (int)d.embedding_dimension;
+  m->p.maxv = d.max;
+  m->p.mean0 = d.mean[0]; m->p.mean1 = d.mean[1]; m->p.mean2 = d.mean[2];
+  m->p.logToneMap = d.log_tone_map;
+  int width = feat;
+  for (uint32_t i = 0; i < d.num_layers; ++i) {
+    const b200rt_nif_layer& L = d.layers[i];
+    LayerDev& o = m->p.layers[i];
+    o.in = (int)L.in_features; o.out = (int)L.out_features; o.relu = L.relu; o.concat = 0;
+    if (!L.kernel_f16 || o.in <= 0 || o.out <= 0) { nif_destroy(m); return bad("bad layer"); }
+    if (o.in != width) {
+      if (o.in == width + feat) o.concat = 1;
+      else { nif_destroy(m); return bad("layer input width matches neither the running width nor width + features"); }
+    }
+    if (o.in > kMaxWidth || o.out > kMaxWidth) { nif_destroy(m); return bad("layer wider than 512"); }
+    width = o.out;
+    void* w = nullptr;
+    const size_t wb = (size_t)o.in * o.out * sizeof(__half);
+    if (cudaMalloc(&w, wb) != cudaSuccess || cudaMemcpy(w, L.kernel_f16, wb, cudaMemcpyHostToDevice) != cudaSuccess) {
+      if (w) cudaFree(w);
+      nif_destroy(m);
+      return bad("cudaMalloc/cudaMemcpy of a NIF kernel failed");
+    }
+    m->allocs.push_back(w);
+    o.w = (const __half*)w;
+    o.b = nullptr;
+    if (L.bias_f16) {
+      void* b = nullptr;
+      const size_t bb = (size_t)o.out * sizeof(__half);
+      if (cudaMalloc(&b, bb) != cudaSuccess || cudaMemcpy(b, L.bias_f16, bb, cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (b) cudaFree(b);
+        nif_destroy(m);
+        return bad("cudaMalloc/cudaMemcpy of a NIF bias failed");
+      }
+      m->allocs.push_back(b);
+      o.b = (const __half*)b;
+    }
+  }
+  if (width != 3) { nif_destroy(m); return bad("last NIF layer must have 3 outputs (b,g,r)"); }
+  return m;
+}
+
+namespace {
+
+// Encode one (u,v) into 4E fp16 features (NifModel.cpp:186-219).
+__device__ __forceinline__ void encode_uv(float u, float v, int E, __half* feat) {
+  const float un = (u - 1.f) * 2.f, vn = (v - 1.f) * 2.f;
+  float c = 1.f;
+  for (int j = 0; j < E; ++j, c *= 2.f) {
+    const float au = __half2float(__float2half_rn(un * c));
+    const float av = __half2float(__float2half_rn(vn * c));
+    feat[j] = __float2half_rn(sinf(au));
+    feat[j + E] = __float2half_rn(sinf(av));
+    feat[j + 2 * E] = __float2half_rn(cosf(au));
+    feat[j + 3 * E] = __float2half_rn(cosf(av));
+  }
+}
+
+// CUDA-core reference implementation of the MLP wavefront: one CTA evaluates kTileRows samples per
+// pass, activations ping-pong between two fp16 shared-memory tiles, each thread owns output columns
+// tid, tid+256, ... and keeps kTileRows fp32 accumulators per column.
+__global__ void __launch_bounds__(kThreads) nif_mlp_kernel(const NifParams p, const float* __restrict__ uvDirect,
+                                                           const float* __restrict__ slotEscape,
+                                                           const uint32_t* __restrict__ queue,
+                                                           const uint32_t* __restrict__ dCount, uint32_t directCount,
+                                                           float* __restrict__ out) {
+  __shared__ __half actA[kTileRows][kMaxWidth + 64];
+  __shared__ __half actB[kTileRows][kMaxWidth + 64];
+  __shared__ __half feat[kTileRows][64];
+  __shared__ uint32_t rowSlot[kTileRows];
+  const uint32_t count = uvDirect ? directCount : min(*dCount, directCount);
+  const int F = 4 * p.embed;
+  for (uint32_t tile = blockIdx.x; (uint64_t)tile * kTileRows < count; tile += gridDim.x) {
+    const uint32_t row0 = tile * kTileRows;
+    __syncthreads();
+    if (threadIdx.x < kTileRows) {
+      const uint32_t r = row0 + threadIdx.x;
+      float u = 0.f, v = 0.f;
+      uint32_t slot = 0xFFFFFFFFu;
+      if (r < count) {
+        if (uvDirect) { slot = r; u = uvDirect[2 * r]; v = uvDirect[2 * r + 1]; }
+        else { slot = queue[r]; u = slotEscape[5 * (size_t)slot + 3]; v = slotEscape[5 * (size_t)slot + 4]; }
+      }
+      rowSlot[threadIdx.x] = slot;
+      encode_uv(u, v, p.embed, feat[threadIdx.x]);
+      for (int k = 0; k < F; ++k) actA[threadIdx.x][k] = feat[threadIdx.x][k];
+    }
+    __syncthreads();
+    __half (*cur)[kMaxWidth + 64] = actA;
+    __half (*nxt)[kMaxWidth + 64] = actB;
+    int width = F;
+    for (int l = 0; l < p.numLayers; ++l) {
+      const LayerDev L = p.layers[l];
+      if (L.concat) {
+        for (int i = threadIdx.x; i < kTileRows * F; i += kThreads) cur[i / F][width + i % F] = feat[i / F][i % F];
+        __syncthreads();
+      }
+      for (int col = threadIdx.x; col < L.out; col += kThreads) {
+        float acc[kTileRows];
+#pragma unroll
+        for (int r = 0; r < kTileRows; ++r) acc[r] = 0.f;
+        for (int k = 0; k < L.in; ++k) {
+          const float w = __half2float(L.w[(size_t)k * L.out + col]);
+#pragma unroll
+          for (int r = 0; r < kTileRows; ++r) acc[r] += __half2float(cur[r][k]) * w;
+        }
+        const float bias = L.b ? __half2float(L.b[col]) : 0.f;
+#pragma unroll
+        for (int r = 0; r < kTileRows; ++r) {
+          float y = acc[r] + bias;
+          if (L.relu) y = y > 0.f ? y : 0.f;
+          nxt[r][col] = __float2half_rn(y);
+        }
+      }
+      __syncthreads();
+      __half (*t)[kMaxWidth + 64] = cur; cur = nxt; nxt = t;
+      width = L.out;
+    }
+    // decode (NifModel.cpp:222-246): fp32 x*max + mean, exp when log-tone-mapped
+    if (threadIdx.x < kTileRows * 3) {
+      const int r = threadIdx.x / 3, c = threadIdx.x % 3;
+      const uint32_t slot = rowSlot[r];
+      if (slot != 0xFFFFFFFFu) {
+        const float mean = c == 0 ? p.mean0 : (c == 1 ? p.mean1 : p.mean2);
+        float y = __half2float(cur[r][c]) * p.maxv + mean;
+        if (p.logToneMap) y = expf(y);
+        out[3 * (size_t)slot + c] = y;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, const uint32_t* queue,
+                  const uint32_t* dCount, uint32_t count, float* out, cudaStream_t stream, int* launches) {
+  if (!m) { g_nifError = "no model"; return -1; }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  const uint32_t tiles = (count + kTileRows - 1) / kTileRows;
+  const uint32_t grid = tiles < (uint32_t)(sms * 4) ? (tiles ? tiles : 1u) : (uint32_t)(sms * 4);
+  nif_mlp_kernel<<<grid, kThreads, 0, stream>>>(m->p, uvDirect, slotEscape, queue, dCount, count, out);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_nifError = cudaGetErrorString(e); return -1; }
+  if (launches) *launches += 1;
+  return 0;
+}
+
+int nif_eval_uv(NifModel* m, const float* dUv, uint32_t n, float* dBgrOut, cudaStream_t stream, int* launches) {
+  return launch(m, dUv, nullptr, nullptr, nullptr, n, dBgrOut, stream, launches);
+}
+
+int nif_eval_queue(NifModel* m, const float* slotEscape, const uint32_t* queue, const uint32_t* dCount,
+                   uint32_t maxCount, float* slotEnv, cudaStream_t stream, int* launches) {
+  return launch(m, nullptr, slotEscape, queue, dCount, maxCount, slotEnv, stream, launches);
+}
+
+}  // namespace rt

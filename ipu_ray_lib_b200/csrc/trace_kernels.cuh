@@ -1,0 +1,353 @@
+// The two render kernels of the trace path.
+//
+//   shadow_trace_kernel : traceShadowRay over a ray stream (include/Render.hpp:37-72; IPU vertex
+//                         ShadowTrace, codelets/TraceCodelets.cpp:269-316)
+//   path_trace_kernel   : per-sample camera ray + the bounce loop (trace.cpp:115-188; IPU vertex
+//                         PathTrace + sampleCameraRays, codelets/TraceCodelets.cpp:142-264)
+//
+// Both are persistent: the grid is sized to the SM count, every warp pulls 32-ray chunks of the
+// TraceResult stream from a global counter until the stream is exhausted. In the path tracer each
+// lane owns one pixel and regenerates its next sample the moment its current path ends, so lanes
+// stay busy through the bounce loop regardless of path length, while rgb is still accumulated in
+// sample order (bit-identical to the sequential reference loop).
+#pragma once
+#include "rt_device.cuh"
+
+namespace rt {
+
+// Word offsets inside the 84-byte TraceResult (include/embree_utils/geometry.hpp:227-260).
+enum : int {
+  TR_RGB = 0, TR_ROW = 3, TR_COL = 4, TR_ORIGIN = 5, TR_TMIN = 8, TR_DIR = 9, TR_TMAX = 12,
+  TR_PRIM = 13, TR_NORMAL = 14, TR_THROUGHPUT = 17, TR_IDS = 20, TR_WORDS = 21
+};
+constexpr uint32_t kFlagError = 1u, kFlagEscaped = 2u;
+
+struct DeviceCounters {
+  unsigned long long closest, occlusion, nodeVisits, primTests, samples, escaped;
+};
+
+struct TraceArgs {
+  DevScene scene;
+  float* rays;              // TraceResult[n] as words
+  uint32_t numRays;
+  uint32_t* workCounter;    // persistent-warp chunk counter (zeroed before launch)
+  DeviceCounters* counters;
+  uint32_t nodeBytes;       // size of the node array when staged into shared memory
+  // shadow trace
+  float lightX, lightY, lightZ, ambient;
+  // path trace
+  float imageWidth, imageHeight, tanTheta, antiAlias;
+  uint32_t maxPathLength, rouletteStartDepth;
+  uint32_t firstSample, endSample;
+  unsigned long long rngKey;  // splitmix64(rngSeed)
+  // NIF wavefront outputs (path trace with an environment light); null otherwise
+  float* slotColor;         // [numRays][samplesPerChunk][3]
+  float* slotEscape;        // [numRays][samplesPerChunk][5] = throughput.xyz, u, v (u < 0: not escaped)
+  uint32_t* escapeQueue;    // compacted slot indices of escaped samples
+  uint32_t* escapeCount;
+  float hdriRotation;       // radians
+};
+
+__device__ __forceinline__ void flush_counters(DeviceCounters* out, unsigned closest, unsigned occl, const Counters& c,
+                                               unsigned samples, unsigned escaped) {
+  // warp-reduce then one atomic per counter per warp
+  unsigned v[6] = {closest, occl, c.nodeVisits, c.primTests, samples, escaped};
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(out);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    unsigned long long x = v[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(dst + k, x);
+  }
+}
+
+template <bool kShared>
+__device__ __forceinline__ const uint2* stage_nodes(const TraceArgs& a, uint2* smem) {
+  if (!kShared) return a.scene.nodes;
+  // cooperative 16-byte copy of the whole node array into shared memory (array is 8 B aligned and a
+  // multiple of 8 B; the device copy is allocated 16 B aligned and padded to 16 B)
+  const uint4* src = reinterpret_cast<const uint4*>(a.scene.nodes);
+  uint4* dst = reinterpret_cast<uint4*>(smem);
+  const uint32_t n16 = (a.nodeBytes + 15u) / 16u;
+  for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+  __syncthreads();
+  return smem;
+}
+
+template <bool kShared, bool kOrdered, bool kCount>
+__device__ __forceinline__ void closest_hit(const DevScene& sc, const uint2* nodes, V3 o, V3 d, float tMin, float tMax,
+                                            Hit& h, Counters& c) {
+  if (kOrdered) closest_hit_ordered<kShared, kCount>(sc, nodes, o, d, tMin, tMax, h, c);
+  else closest_hit_ref_order<kShared, kCount>(sc, nodes, o, d, tMin, tMax, h, c);
+}
+
+// -------------------------------------------------------------------------------------------------
+template <bool kShared, bool kOrdered, bool kCount>
+__global__ void __launch_bounds__(512) shadow_trace_kernel(const TraceArgs a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const uint2* nodes = stage_nodes<kShared>(a, reinterpret_cast<uint2*>(smemRaw));
+  const DevScene& sc = a.scene;
+  const unsigned lane = threadIdx.x & 31;
+  const V3 light = mk(a.lightX, a.lightY, a.lightZ);
+  Counters cnt = {0u, 0u};
+  unsigned nClosest = 0, nOccl = 0;
+
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.workCounter, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= a.numRays) break;
+    const uint32_t idx = base + lane;
+    if (idx >= a.numRays) continue;
+    float* tr = a.rays + (size_t)idx * TR_WORDS;
+
+    V3 o = mk(tr[TR_ORIGIN], tr[TR_ORIGIN + 1], tr[TR_ORIGIN + 2]);
+    const V3 d = mk(tr[TR_DIR], tr[TR_DIR + 1], tr[TR_DIR + 2]);
+    const float tMin = tr[TR_TMIN], tMax = tr[TR_TMAX];
+    Hit h;
+    nClosest++;
+    closest_hit<kShared, kOrdered, kCount>(sc, nodes, o, d, tMin, tMax, h, cnt);
+    if (h.geomID != kInvalidGeom) {
+      // updateHit (Render.hpp:15-23)
+      o = o + d * h.t;
+      const V3 n = hit_normal(sc, h, o);
+      const Mat m = load_material(sc, h.geomID);
+      // shadow ray towards the light (Render.hpp:50-60); tMax is the distance BEFORE the offset
+      const V3 lightOffset = light - o;
+      const V3 sd = normalized(lightOffset);
+      const V3 so = offset_origin(o, sd, n);
+      const float sMax = sqrtf(norm2(lightOffset));
+      V3 color = m.albedo * a.ambient;
+      nOccl++;
+      if (!any_hit<kShared, kCount>(sc, nodes, so, sd, 0.f, sMax, cnt)) color = color + m.albedo * dot(sd, n);
+      tr[TR_RGB] = color.x; tr[TR_RGB + 1] = color.y; tr[TR_RGB + 2] = color.z;
+      tr[TR_ORIGIN] = o.x; tr[TR_ORIGIN + 1] = o.y; tr[TR_ORIGIN + 2] = o.z;
+      tr[TR_TMAX] = h.t;
+      tr[TR_PRIM] = __uint_as_float(h.primID);
+      tr[TR_NORMAL] = n.x; tr[TR_NORMAL + 1] = n.y; tr[TR_NORMAL + 2] = n.z;
+      const uint32_t ids = __float_as_uint(tr[TR_IDS]);
+      tr[TR_IDS] = __uint_as_float((ids & 0xffff0000u) | h.geomID);
+    } else {
+      const uint32_t ids = __float_as_uint(tr[TR_IDS]);
+      tr[TR_IDS] = __uint_as_float(ids | (kFlagEscaped << 16));
+    }
+  }
+  flush_counters(a.counters, nClosest, nOccl, cnt, 0u, 0u);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Equirectangular (u,v) of an escaped direction (PreProcessEscapedRays, codelets/TraceCodelets.cpp:337-348).
+__device__ __forceinline__ void escaped_uv(V3 d, float rotation, float& u, float& v) {
+  const float theta = acosf(d.y);
+  float phi = atan2f(d.z, d.x) + rotation;
+  const float twoPi = 6.28318530717958647692f;
+  if (phi < 0.f) phi += twoPi;
+  else if (phi > twoPi) phi -= twoPi;
+  u = theta * 0.31830988618379067154f;
+  v = phi * 0.15915494309189533577f;
+}
+
+template <bool kShared, bool kOrdered, bool kCount, bool kNif>
+__global__ void __launch_bounds__(512) path_trace_kernel(const TraceArgs a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const uint2* nodes = stage_nodes<kShared>(a, reinterpret_cast<uint2*>(smemRaw));
+  const DevScene& sc = a.scene;
+  const unsigned lane = threadIdx.x & 31;
+  const float inf = __int_as_float(0x7f800000);
+  const uint32_t chunk = a.endSample - a.firstSample;
+  Counters cnt = {0u, 0u};
+  unsigned nClosest = 0, nSamples = 0, nEscaped = 0;
+
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.workCounter, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= a.numRays) break;
+    const uint32_t idx = base + lane;
+    if (idx >= a.numRays) continue;
+    float* tr = a.rays + (size_t)idx * TR_WORDS;
+
+    const float row = tr[TR_ROW], col = tr[TR_COL];
+    const uint32_t pixelIndex = (uint32_t)row * (uint32_t)a.imageWidth + (uint32_t)col;
+    V3 rgb = mk(tr[TR_RGB], tr[TR_RGB + 1], tr[TR_RGB + 2]);
+
+    // per-path state (HitRecord fields + loop variables)
+    V3 o, d, n, thr, color;
+    float tMaxOut = inf;
+    uint32_t primID = kInvalidPrim, geomID = kInvalidGeom, flags = 0;
+    Rng rng;
+    uint32_t s = a.firstSample;
+    uint32_t bounce = 0;
+    bool fresh = true;
+
+    while (true) {
+      if (fresh) {
+        if (s == a.endSample) break;
+        // sampleCameraRays (codelets/TraceCodelets.cpp:142-164) with the per-(pixel,sample) stream
+        rng_seed_stream(rng, a.rngKey, pixelIndex, s);
+        const uint64_t ra = rng_next(rng), rb = rng_next(rng);
+        float g0, g1;
+        gaussian_pair(ra, rb, g0, g1);
+        const float pu = row + a.antiAlias * g0;
+        const float pv = col + a.antiAlias * g1;
+        d = pixel_to_ray_dir(pv, pu, a.imageWidth, a.imageHeight, a.tanTheta);
+        o = mk(0.f, 0.f, 0.f);
+        n = mk(0.f, 0.f, 1.f);
+        primID = kInvalidPrim; geomID = kInvalidGeom; flags = 0;
+        thr = mk(1.f, 1.f, 1.f);
+        color = mk(0.f, 0.f, 0.f);
+        bounce = 0;
+        fresh = false;
+        nSamples++;
+      }
+
+      // ---- one iteration of the bounce loop (trace.cpp:125-184) ----
+      bool ended = false, escaped = false;
+      o = offset_origin(o, d, n);
+      Hit h;
+      nClosest++;
+      closest_hit<kShared, kOrdered, kCount>(sc, nodes, o, d, 0.f, inf, h, cnt);
+      tMaxOut = h.t;
+      if (h.geomID != kInvalidGeom) {
+        geomID = h.geomID; primID = h.primID;
+        o = o + d * h.t;
+        n = hit_normal(sc, h, o);
+        const Mat m = load_material(sc, geomID);
+        if (m.emissive) color = color + thr * m.emission;
+        if (m.type == 0) {
+          const float u1 = rng_uniform(rng);
+          const float u2 = rng_uniform(rng);
+          d = sample_diffuse(n, u1, u2);
+          thr = thr * m.albedo;
+        } else if (m.type == 1) {
+          d = reflect_dir(d, n);
+          thr = thr * m.albedo;
+        } else if (m.type == 2) {
+          const float u1 = rng_uniform(rng);
+          bool refracted;
+          d = dielectric_dir(d, n, m.ior, u1, refracted);
+          if (refracted) thr = thr * m.albedo;
+        } else {
+          rgb = rgb * __int_as_float(0x7fc00000);  // result.rgb *= NaN (trace.cpp:167)
+          flags |= kFlagError;
+        }
+      } else {
+        flags |= kFlagEscaped;
+        ended = true;
+        escaped = true;
+      }
+      if (!ended) {
+        if (bounce > a.rouletteStartDepth) {
+          const float u1 = rng_uniform(rng);
+          const float p = maxc(thr);  // evaluateRoulette (geometric_sampling.hpp:56-63)
+          if (p == 0.f || u1 > p) ended = true;
+          else thr = thr * (1.f / p);
+        }
+        bounce++;
+        if (bounce >= a.maxPathLength) ended = true;
+      }
+
+      if (ended) {
+        if (escaped) nEscaped++;
+        if (kNif) {
+          // wavefront hand-off: the environment light is evaluated by the NIF kernel afterwards and
+          // rgb is accumulated in sample order by accumulate_kernel
+          const size_t slot = (size_t)idx * chunk + (s - a.firstSample);
+          float* sc3 = a.slotColor + 3 * slot;
+          sc3[0] = color.x; sc3[1] = color.y; sc3[2] = color.z;
+          float* se = a.slotEscape + 5 * slot;
+          float u = -1.f, v = 0.f;
+          if (escaped) escaped_uv(d, a.hdriRotation, u, v);
+          se[0] = thr.x; se[1] = thr.y; se[2] = thr.z; se[3] = u; se[4] = v;
+          // compact escaped slots (warp-aggregated append)
+          const unsigned active = __activemask();
+          const unsigned mask = __ballot_sync(active, escaped);
+          if (escaped) {
+            const int leader = __ffs(mask) - 1;
+            uint32_t qbase = 0;
+            if ((int)lane == leader) qbase = atomicAdd(a.escapeCount, (uint32_t)__popc(mask));
+            qbase = __shfl_sync(mask, qbase, leader);
+            a.escapeQueue[qbase + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)slot;
+          }
+        } else {
+          rgb = rgb + color;  // result.rgb += color (trace.cpp:187)
+        }
+        s++;
+        fresh = true;
+      }
+    }
+
+    // write back: rgb running sum + the HitRecord of the last sample (what the reference leaves behind)
+    if (!kNif) { tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z; }
+    if (a.endSample > a.firstSample) {
+      tr[TR_ORIGIN] = o.x; tr[TR_ORIGIN + 1] = o.y; tr[TR_ORIGIN + 2] = o.z;
+      tr[TR_TMIN] = 0.f;
+      tr[TR_DIR] = d.x; tr[TR_DIR + 1] = d.y; tr[TR_DIR + 2] = d.z;
+      tr[TR_TMAX] = tMaxOut;
+      tr[TR_PRIM] = __uint_as_float(primID);
+      tr[TR_NORMAL] = n.x; tr[TR_NORMAL + 1] = n.y; tr[TR_NORMAL + 2] = n.z;
+      tr[TR_THROUGHPUT] = thr.x; tr[TR_THROUGHPUT + 1] = thr.y; tr[TR_THROUGHPUT + 2] = thr.z;
+      tr[TR_IDS] = __uint_as_float(geomID | (flags << 16));
+    }
+  }
+  flush_counters(a.counters, nClosest, 0u, cnt, nSamples, nEscaped);
+}
+
+// rgb += color_s; rgb += throughput_s * (bgr[2], bgr[1], bgr[0]) for s in chunk order
+// (PathTrace `result.rgb += color` followed by PostProcessEscapedRays, codelets/TraceCodelets.cpp:257, :361-382).
+__global__ void accumulate_kernel(float* rays, uint32_t numRays, uint32_t chunk, const float* slotColor,
+                                  const float* slotEscape, const float* slotEnv) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= numRays) return;
+  float* tr = rays + (size_t)idx * TR_WORDS;
+  V3 rgb = mk(tr[TR_RGB], tr[TR_RGB + 1], tr[TR_RGB + 2]);
+  for (uint32_t c = 0; c < chunk; ++c) {
+    const size_t slot = (size_t)idx * chunk + c;
+    const float* col = slotColor + 3 * slot;
+    rgb = rgb + mk(col[0], col[1], col[2]);
+    const float* se = slotEscape + 5 * slot;
+    if (se[3] >= 0.f) {
+      const float* env = slotEnv + 3 * slot;
+      rgb = rgb + mk(se[0], se[1], se[2]) * mk(env[2], env[1], env[0]);
+    }
+  }
+  tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z;
+}
+
+// Bare-ray queries for the parity tests (b200rt_intersect / b200rt_occluded).
+struct QueryHit {
+  float t;
+  uint32_t geomID, primID;
+  float nx, ny, nz;
+};
+template <bool kOrdered>
+__global__ void intersect_kernel(DevScene sc, const float* rays, uint32_t n, QueryHit* out, DeviceCounters* counters) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  Counters cnt = {0u, 0u};
+  unsigned nq = 0;
+  if (idx < n) {
+    const float* r = rays + 8 * (size_t)idx;
+    const V3 o = mk(r[0], r[1], r[2]), d = mk(r[4], r[5], r[6]);
+    Hit h;
+    nq = 1;
+    closest_hit<false, kOrdered, true>(sc, sc.nodes, o, d, r[3], r[7], h, cnt);
+    QueryHit q;
+    q.t = h.t; q.geomID = h.geomID; q.primID = h.primID; q.nx = q.ny = q.nz = 0.f;
+    if (h.geomID != kInvalidGeom) {
+      const V3 nn = hit_normal(sc, h, o + d * h.t);
+      q.nx = nn.x; q.ny = nn.y; q.nz = nn.z;
+    }
+    out[idx] = q;
+  }
+  flush_counters(counters, nq, 0u, cnt, 0u, 0u);
+}
+__global__ void occluded_kernel(DevScene sc, const float* rays, uint32_t n, unsigned char* out) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float* r = rays + 8 * (size_t)idx;
+  Counters cnt = {0u, 0u};
+  out[idx] = any_hit<false, false>(sc, sc.nodes, mk(r[0], r[1], r[2]), mk(r[4], r[5], r[6]), r[3], r[7], cnt) ? 1 : 0;
+}
+
+}  // namespace rt

@@ -1,0 +1,119 @@
+"""NIF environment-light weights: container, synthetic generator and file format.
+
+The reference loads a Keras HDF5 file (src/keras/Hdf5Model.cpp) that is missing from its checkout
+(.MISSING_LARGE_BLOBS) and whose reader needs libhdf5 (absent here). This module keeps the layer
+list data-driven exactly like the reference (a list of Dense layers: fp16 kernel [in,out],
+optional fp16 bias, relu/linear) and provides
+  * ``NifWeights.synthetic`` — fixed-seed random weights in the architecture the shipped metadata
+    implies (embedding 12, hidden 320, 6 hidden layers with the encoded input concatenated into the
+    4th, 3 linear outputs), and
+  * a trivial ``.npz`` container so trained weights exported from Keras can be dropped in.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+from . import _capi as capi
+
+
+@dataclass
+class DenseLayer:
+    kernel: np.ndarray            # [in, out] float16
+    bias: np.ndarray | None       # [out] float16
+    relu: bool
+
+
+@dataclass
+class NifWeights:
+    embedding_dimension: int
+    layers: list = field(default_factory=list)
+    max: float = 3.4299468994140625
+    mean: tuple = (-2.3514461517333984 - 1e-8, -2.2660605907440186 - 1e-8, -1.9648972749710083 - 1e-8)
+    log_tone_map: bool = True
+
+    @classmethod
+    def synthetic(cls, seed: int = 1442, embedding_dimension: int = 12, hidden: int = 320,
+                  hidden_layers: int = 6, concat_at: int = 3, scale: float = 1.0) -> "NifWeights":
+        rng = np.random.default_rng(seed)
+        feat = 4 * embedding_dimension
+        w = cls(embedding_dimension=embedding_dimension)
+        width = feat
+        for i in range(hidden_layers):
+            k_in = width + (feat if i == concat_at else 0)
+            kern = (rng.standard_normal((k_in, hidden)) * (scale * np.sqrt(2.0 / k_in))).astype(np.float16)
+            bias = (rng.standard_normal(hidden) * 0.05).astype(np.float16)
+            w.layers.append(DenseLayer(kern, bias, True))
+            width = hidden
+        kern = (rng.standard_normal((width, 3)) * (0.5 / np.sqrt(width))).astype(np.float16)
+        bias = (rng.standard_normal(3) * 0.1).astype(np.float16)
+        w.layers.append(DenseLayer(kern, bias, False))
+        return w
+
+    @classmethod
+    def from_metadata(cls, metadata_path, seed: int = 1442, **kw) -> "NifWeights":
+        """Synthetic weights shaped by a nif_metadata.txt (IpuScene::loadNifModel, src/IpuScene.cpp:174-187)."""
+        md = capi.NifMetadata()
+        rc = capi.scene_lib().b200rt_read_nif_metadata(str(metadata_path).encode(), C.byref(md))
+        if rc != 0:
+            raise RuntimeError(capi.scene_lib().b200rt_scene_last_error().decode())
+        w = cls.synthetic(seed=seed, embedding_dimension=md.embedding_dimension, hidden=md.hidden_size or 320, **kw)
+        w.max = float(md.max)
+        w.mean = tuple(float(x) for x in md.mean)
+        w.log_tone_map = bool(md.log_tone_map)
+        return w
+
+    def save(self, path) -> None:
+        arrays = {"embedding_dimension": np.int32(self.embedding_dimension), "max": np.float32(self.max),
+                  "mean": np.asarray(self.mean, np.float32), "log_tone_map": np.int32(self.log_tone_map),
+                  "num_layers": np.int32(len(self.layers))}
+        for i, l in enumerate(self.layers):
+            arrays[f"kernel_{i}"] = l.kernel
+            arrays[f"relu_{i}"] = np.int32(l.relu)
+            if l.bias is not None:
+                arrays[f"bias_{i}"] = l.bias
+        np.savez(path, **arrays)
+
+    @classmethod
+    def load(cls, path) -> "NifWeights":
+        z = np.load(path)
+        w = cls(embedding_dimension=int(z["embedding_dimension"]), max=float(z["max"]),
+                mean=tuple(float(x) for x in z["mean"]), log_tone_map=bool(z["log_tone_map"]))
+        for i in range(int(z["num_layers"])):
+            bias = z[f"bias_{i}"].astype(np.float16) if f"bias_{i}" in z else None
+            w.layers.append(DenseLayer(z[f"kernel_{i}"].astype(np.float16), bias, bool(z[f"relu_{i}"])))
+        return w
+
+    def flops_per_sample(self) -> int:
+        """sum(2*K*N + N_bias) as NifModel::analyseModel (src/neural_networks/NifModel.cpp:123-145)."""
+        return sum(2 * l.kernel.shape[0] * l.kernel.shape[1] + (l.kernel.shape[1] if l.bias is not None else 0)
+                   for l in self.layers)
+
+    def to_desc(self):
+        """(b200rt_nif_desc, keepalive) for the C ABI / oracle."""
+        n = len(self.layers)
+        arr = (capi.NifLayer * n)()
+        keep = [arr]
+        for i, l in enumerate(self.layers):
+            k = np.ascontiguousarray(l.kernel, dtype=np.float16)
+            keep.append(k)
+            arr[i].in_features, arr[i].out_features = k.shape
+            arr[i].kernel_f16 = k.ctypes.data
+            if l.bias is not None:
+                b = np.ascontiguousarray(l.bias, dtype=np.float16)
+                keep.append(b)
+                arr[i].bias_f16 = b.ctypes.data
+            else:
+                arr[i].bias_f16 = None
+            arr[i].relu = int(l.relu)
+        d = capi.NifDesc()
+        d.embedding_dimension = self.embedding_dimension
+        d.num_layers = n
+        d.layers = C.cast(arr, C.POINTER(capi.NifLayer))
+        d.max = self.max
+        d.mean[0], d.mean[1], d.mean[2] = self.mean
+        d.log_tone_map = int(self.log_tone_map)
+        return d, keep
