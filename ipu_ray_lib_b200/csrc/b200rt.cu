@@ -45,7 +45,7 @@ struct DeviceBuffer {
     if (e != cudaSuccess) return e;
     e = cudaMemset(p, 0, bytes);
     if (e != cudaSuccess) return e;
-    if (n) e = cudaMemcpy(p, src, n, cudaMemcpyHostToDevice);
+    if (n && src) e = cudaMemcpy(p, src, n, cudaMemcpyHostToDevice);
     return e;
   }
   cudaError_t reserve(size_t n) {
