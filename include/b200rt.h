@@ -103,7 +103,11 @@ typedef struct b200rt_trace_stats {
   double   h2d_ms, d2h_ms;        /* host<->device copies of the ray stream (host-buffer entry points only) */
   double   trace_secs;            /* wall time; same span as IpuScene::getTraceTimeSecs (src/IpuScene.cpp:672-696) */
   uint64_t kernel_launches;       /* number of kernels this library launched */
-  uint64_t reserved[4];
+  double   trace_kernel_ms;       /* sum over launches of shadow_trace / path_trace kernel time (CUDA events) */
+  double   nif_kernel_ms;         /* sum over launches of the NIF MLP kernel time */
+  double   accumulate_kernel_ms;  /* sum over launches of the ordered rgb accumulation kernel */
+  uint64_t trace_kernel_launches, nif_kernel_launches;
+  uint64_t reserved[2];
 } b200rt_trace_stats;
 
 /* Called once per finished ray batch with (batch_index, rays, n, user).

@@ -88,7 +88,9 @@ class TraceStats(C.Structure):
         ("samples", C.c_uint64), ("escaped_samples", C.c_uint64),
         ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("trace_secs", C.c_double), ("kernel_launches", C.c_uint64),
-        ("reserved", C.c_uint64 * 4),
+        ("trace_kernel_ms", C.c_double), ("nif_kernel_ms", C.c_double), ("accumulate_kernel_ms", C.c_double),
+        ("trace_kernel_launches", C.c_uint64), ("nif_kernel_launches", C.c_uint64),
+        ("reserved", C.c_uint64 * 2),
     ]
 
 

@@ -192,6 +192,33 @@ cudaError_t run_path(b200rt_scene& sc, const LaunchPlan& L, bool nif, const rt::
                    : dispatch_path<false, false>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream);
 }
 
+// Per-kernel device timing with CUDA event pairs recorded on the launching stream.
+struct KernelTimer {
+  enum Kind { TRACE = 0, NIF = 1, ACCUM = 2 };
+  struct Span { cudaEvent_t a, b; Kind kind; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+  void begin(Kind k, cudaStream_t st) { Span s{get(), get(), k}; cudaEventRecord(s.a, st); spans.push_back(s); }
+  void end(cudaStream_t st) { cudaEventRecord(spans.back().b, st); }
+  void collect(b200rt_trace_stats& out) {
+    for (const Span& s : spans) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, s.a, s.b) != cudaSuccess) continue;
+      if (s.kind == TRACE) { out.trace_kernel_ms += ms; out.trace_kernel_launches += 1; }
+      else if (s.kind == NIF) { out.nif_kernel_ms += ms; out.nif_kernel_launches += 1; }
+      else out.accumulate_kernel_ms += ms;
+    }
+    spans.clear();
+    used = 0;
+  }
+  ~KernelTimer() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
+};
+
 float host_tan_half_fov(float fov) {
   float s, c;
   rt::sincos_tbl(fov / 2.f, s, c);
@@ -217,6 +244,7 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
   CU_TRY(cudaMemsetAsync(sc.counters.p, 0, sizeof(rt::DeviceCounters), sc.stream));
   CU_TRY(cudaEventRecord(sc.evStart, sc.stream));
   uint64_t launches = 0;
+  KernelTimer timer;
 
   if (!sc.desc.path_trace) {
     const bool dflt = p.light_pos[0] == 0.f && p.light_pos[1] == 0.f && p.light_pos[2] == 0.f && p.ambient == 0.f;
@@ -225,7 +253,9 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
     a.lightZ = dflt ? -1060.f : p.light_pos[2];
     a.ambient = dflt ? .05f : p.ambient;
     CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
+    timer.begin(KernelTimer::TRACE, sc.stream);
     CU_TRY(run_shadow(sc, L, a));
+    timer.end(sc.stream);
     launches += 1;
   } else {
     if (!(sc.desc.image_width >= 1.f) || !(sc.desc.image_height >= 1.f))
@@ -243,7 +273,9 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
       a.firstSample = first;
       a.endSample = first + count;
       CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
+      timer.begin(KernelTimer::TRACE, sc.stream);
       CU_TRY(run_path(sc, L, false, a));
+      timer.end(sc.stream);
       launches += 1;
     } else {
       // Wavefront over chunks of samples: trace -> (compacted escaped rays) NIF -> ordered accumulate.
@@ -268,17 +300,23 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
         a.endSample = s0 + c;
         CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
         CU_TRY(cudaMemsetAsync(sc.escapeCount.p, 0, 4, sc.stream));
+        timer.begin(KernelTimer::TRACE, sc.stream);
         CU_TRY(run_path(sc, L, true, a));
+        timer.end(sc.stream);
         launches += 1;
         int nifLaunches = 0;
+        timer.begin(KernelTimer::NIF, sc.stream);
         const int rc = rt::nif_eval_queue(sc.nif, (const float*)sc.slotEscape.p, (const uint32_t*)sc.escapeQueue.p,
                                           (const uint32_t*)sc.escapeCount.p, (uint32_t)std::min<size_t>((size_t)c * n, 0xFFFFFFFFull),
                                           (float*)sc.slotEnv.p, sc.stream, &nifLaunches);
+        timer.end(sc.stream);
         if (rc != 0) return fail(B200RT_ERR_CUDA, std::string("NIF evaluation failed: ") + rt::nif_last_error());
         launches += (uint64_t)nifLaunches;
         const uint32_t threads = 256, blocks = (uint32_t)((n + threads - 1) / threads);
+        timer.begin(KernelTimer::ACCUM, sc.stream);
         rt::accumulate_kernel<<<blocks, threads, 0, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,
                                                                  (const float*)sc.slotEscape.p, (const float*)sc.slotEnv.p);
+        timer.end(sc.stream);
         CU_TRY(cudaGetLastError());
         launches += 1;
       }
@@ -288,6 +326,7 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
   CU_TRY(cudaStreamSynchronize(sc.stream));
   float ms = 0.f;
   CU_TRY(cudaEventElapsedTime(&ms, sc.evStart, sc.evStop));
+  timer.collect(sc.stats);
   rt::DeviceCounters hc{};
   CU_TRY(cudaMemcpy(&hc, sc.counters.p, sizeof(hc), cudaMemcpyDeviceToHost));
   sc.stats.closest_hit_queries += hc.closest;

@@ -1,0 +1,262 @@
+// B200Scene — C++ mirror of the reference's `IpuScene` (include/IpuScene.hpp:22-112) over the C ABI.
+//
+// Same public surface, same call order as renderIPU (trace.cpp:270-336):
+//     B200Scene scene(spheres, discs, sceneRef, rayStream, raysPerWorker, callbackPtr);
+//     scene.setRuntimeConfig({numGpus});            // ipus -> GPUs, one replica per device
+//     scene.loadNifModel(path); scene.setHdriRotation(deg); scene.setMaxNifBatchSize(n);
+//     int rc = scene.run();                         // GraphManager().run(scene, opts)
+//     scene.getTraceTimeSecs();
+// Batching follows src/IpuScene.cpp:78-172: the stream is cut into batches of
+// raysPerWorker * 6 * 1440 rays, batch i belongs to replica i % R, and a registered callback sees
+// (batchIndex, batch) with the reference's numbering. Replicas run concurrently, one host thread per
+// GPU; results are written back in place into the caller's ray stream.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200rt.h"
+#include "../../include/b200rt_scene.h"
+#include "rt_types.hpp"
+
+namespace b200rt {
+
+// `SceneRef` (include/Scene.hpp:50-74): non-owning views + render parameters.
+struct SceneRef {
+  const HostScene* data = nullptr;
+  float imageWidth = 0, imageHeight = 0, fovRadians = 0, antiAliasScale = .25f;
+  std::uint32_t maxPathLength = 10, rouletteStartDepth = 3, samplesPerPixel = 256;
+  std::uint64_t rngSeed = 1442;
+  CropWindow window{0, 0, 0, 0};
+  bool pathTrace = true;
+};
+
+struct RuntimeConfig {  // ipu_utils::RuntimeConfig (include/ipu_utils.hpp:174-183), the fields that still mean something
+  std::uint32_t numGpus = 1;
+  std::uint32_t numReplicas = 1;
+};
+
+// NIF weights in the library's own container (the reference's Keras HDF5 needs libhdf5, absent here):
+//   "B2NF" u32 version=1 u32 embedding u32 numLayers f32 max f32 mean[3] u32 logToneMap
+//   per layer: u32 in, u32 out, u32 relu, u32 hasBias, fp16 kernel[in*out], fp16 bias[out]
+struct NifWeightsFile {
+  std::uint32_t embedding = 12;
+  float max = 0.f, mean[3] = {0, 0, 0};
+  std::uint32_t logToneMap = 1;
+  struct Layer { std::uint32_t in, out, relu; std::vector<std::uint16_t> kernel, bias; };
+  std::vector<Layer> layers;
+
+  static NifWeightsFile load(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("Could not open NIF weights '" + path + "'");
+    auto rd = [&](void* p, size_t n) { if (!f.read((char*)p, (std::streamsize)n)) throw std::runtime_error("truncated NIF weights file"); };
+    char magic[4];
+    std::uint32_t version, n;
+    NifWeightsFile w;
+    rd(magic, 4); rd(&version, 4); rd(&w.embedding, 4); rd(&n, 4); rd(&w.max, 4); rd(w.mean, 12); rd(&w.logToneMap, 4);
+    if (std::memcmp(magic, "B2NF", 4) != 0 || version != 1 || n > 16) throw std::runtime_error("bad NIF weights header");
+    w.layers.resize(n);
+    for (auto& L : w.layers) {
+      std::uint32_t hasBias;
+      rd(&L.in, 4); rd(&L.out, 4); rd(&L.relu, 4); rd(&hasBias, 4);
+      if ((std::uint64_t)L.in * L.out > (1u << 24)) throw std::runtime_error("implausible NIF layer shape");
+      L.kernel.resize((size_t)L.in * L.out);
+      rd(L.kernel.data(), L.kernel.size() * 2);
+      if (hasBias) { L.bias.resize(L.out); rd(L.bias.data(), L.bias.size() * 2); }
+    }
+    return w;
+  }
+};
+
+class B200Scene {
+ public:
+  using RayCallbackFn = std::function<void(std::size_t, const std::vector<TraceResult>&)>;
+
+  B200Scene(const std::vector<SphereData>& spheres, const std::vector<DiscData>& discs, SceneRef& sceneRef,
+            std::vector<TraceResult>& results, std::size_t raysPerWorker, RayCallbackFn* fn = nullptr)
+      : spheres_(spheres), discs_(discs), data_(sceneRef), rayStream_(results), rayFunc_(fn),
+        maxRaysPerWorker_(raysPerWorker ? raysPerWorker : 1) {}
+
+  void setRuntimeConfig(const RuntimeConfig& c) { config_ = c; }
+  const RuntimeConfig& getRuntimeConfig() const { return config_; }
+
+  // IpuScene::loadNifModel (src/IpuScene.cpp:174-187): metadata + weights from the assets.extra directory.
+  bool loadNifModel(const std::string& assetPath) {
+    try {
+      b200rt_nif_metadata md{};
+      if (b200rt_read_nif_metadata((assetPath + "/nif_metadata.txt").c_str(), &md) != 0)
+        throw std::runtime_error(b200rt_scene_last_error());
+      nif_ = NifWeightsFile::load(assetPath + "/converted.b200nif");
+      nif_.max = md.max;
+      std::copy(md.mean, md.mean + 3, nif_.mean);
+      nif_.logToneMap = (std::uint32_t)md.log_tone_map;
+      nif_.embedding = md.embedding_dimension;
+      haveNif_ = true;
+      std::fprintf(stderr, "[info] Loaded NIF model from '%s'\n", assetPath.c_str());
+      return true;
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "[error] Could not load NIF model from '%s'. Exception: %s\n", assetPath.c_str(), e.what());
+    }
+    return false;
+  }
+  void setNifWeights(const NifWeightsFile& w) { nif_ = w; haveNif_ = true; }
+  void setHdriRotation(float degrees) { hdriRotationDegrees_ = degrees; }
+  void setAvailableMemoryProportion(float) {}  // IPU matmul planner knob; accepted and ignored
+  void setMaxNifBatchSize(std::size_t n) { nifMaxRaysPerBatch_ = n; }
+
+  double getTraceTimeSecs() const { return traceTimeSecs_; }
+  RayCallbackFn* getRayCallback() { return rayFunc_; }
+  std::vector<std::vector<TraceResult>>& getRayBatches() { return rayBatches_; }
+  std::size_t getRayStreamSize() const { return raysPerBatch() * sizeof(TraceResult); }
+  const b200rt_trace_stats& getStats() const { return stats_; }
+
+  // ipu_utils::GraphManager::run (include/ipu_utils.hpp:531-596): everything in one call, exceptions -> EXIT_FAILURE.
+  int run() {
+    try {
+      execute();
+      return EXIT_SUCCESS;
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "[error] Exception: %s\n", e.what());
+      return EXIT_FAILURE;
+    }
+  }
+
+ private:
+  std::size_t raysPerBatch() const { return maxRaysPerWorker_ * 6 * 1440; }  // workers x compute tiles of one Mk2 IPU
+
+  b200rt_scene_desc makeDesc(int device) const {
+    const HostScene& h = *data_.data;
+    b200rt_scene_desc d{};
+    d.geometry = h.geometry.data(); d.num_geometry = (std::uint32_t)h.geometry.size();
+    d.mesh_info = h.meshInfo.data(); d.num_meshes = (std::uint32_t)h.meshInfo.size();
+    d.mesh_tris = h.meshTris.data(); d.num_tris = (std::uint32_t)h.meshTris.size();
+    d.mesh_verts = h.meshVerts.data(); d.num_verts = (std::uint32_t)h.meshVerts.size();
+    d.mesh_normals = h.meshNormals.data(); d.num_normals = (std::uint32_t)h.meshNormals.size();
+    d.mat_ids = h.matIDs.data(); d.num_mat_ids = (std::uint32_t)h.matIDs.size();
+    d.materials = h.materials.data(); d.num_materials = (std::uint32_t)h.materials.size();
+    d.bvh_nodes = h.bvhNodes.data(); d.num_bvh_nodes = (std::uint32_t)h.bvhNodes.size();
+    d.max_leaf_depth = h.bvhMaxDepth;
+    d.spheres = (const float*)spheres_.data(); d.num_spheres = (std::uint32_t)spheres_.size();
+    d.discs = (const float*)discs_.data(); d.num_discs = (std::uint32_t)discs_.size();
+    d.image_width = data_.imageWidth; d.image_height = data_.imageHeight;
+    d.fov_radians = data_.fovRadians; d.anti_alias_scale = data_.antiAliasScale;
+    d.max_path_length = data_.maxPathLength; d.roulette_start_depth = data_.rouletteStartDepth;
+    d.samples_per_pixel = data_.samplesPerPixel; d.rng_seed = data_.rngSeed;
+    d.path_trace = data_.pathTrace ? 1 : 0;
+    d.device = device;
+    return d;
+  }
+
+  struct CallbackCtx {
+    B200Scene* self;
+    std::size_t replica, numReplicas;
+  };
+  static void trampoline(std::size_t localIndex, const void* rays, std::size_t n, void* user) {
+    auto* ctx = (CallbackCtx*)user;
+    const std::size_t batchIndex = localIndex * ctx->numReplicas + ctx->replica;  // RayCallback::fetch numbering
+    auto& batch = ctx->self->rayBatches_[batchIndex];
+    std::memcpy(batch.data(), rays, n * sizeof(TraceResult));
+    (*ctx->self->rayFunc_)(batchIndex, batch);
+  }
+
+  void execute() {
+    const int available = b200rt_device_count();
+    if (available < 1) throw std::runtime_error("no B200 device available (there is no CPU fallback for this path)");
+    const std::size_t R = std::max<std::uint32_t>(1, std::min<std::uint32_t>(config_.numGpus, (std::uint32_t)available));
+    const std::size_t per = raysPerBatch();
+    const std::size_t numBatches = (rayStream_.size() + per - 1) / per;
+    // createRayBatches (src/IpuScene.cpp:110-172) without the dud-ray padding the IPU graph needed
+    rayBatches_.assign(numBatches, {});
+    for (std::size_t b = 0; b < numBatches; ++b) {
+      const std::size_t lo = b * per, hi = std::min(rayStream_.size(), lo + per);
+      rayBatches_[b].assign(rayStream_.begin() + (long)lo, rayStream_.begin() + (long)hi);
+    }
+    // gather each replica's batches (i % R) into one contiguous stream so a replica fills its GPU
+    std::vector<std::vector<TraceResult>> perReplica(R);
+    for (std::size_t b = 0; b < numBatches; ++b)
+      perReplica[b % R].insert(perReplica[b % R].end(), rayBatches_[b].begin(), rayBatches_[b].end());
+
+    std::vector<std::string> errors(R);
+    std::vector<b200rt_trace_stats> stats(R);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> threads;
+    for (std::size_t r = 0; r < R; ++r) {
+      threads.emplace_back([&, r] {
+        b200rt_scene* sc = nullptr;
+        const b200rt_scene_desc d = makeDesc((int)r);
+        if (b200rt_scene_create(&d, &sc) != 0) { errors[r] = b200rt_last_error(); return; }
+        if (haveNif_ && data_.pathTrace) {
+          std::vector<b200rt_nif_layer> layers(nif_.layers.size());
+          for (std::size_t i = 0; i < layers.size(); ++i) {
+            layers[i].in_features = nif_.layers[i].in; layers[i].out_features = nif_.layers[i].out;
+            layers[i].kernel_f16 = nif_.layers[i].kernel.data();
+            layers[i].bias_f16 = nif_.layers[i].bias.empty() ? nullptr : nif_.layers[i].bias.data();
+            layers[i].relu = (std::int32_t)nif_.layers[i].relu;
+          }
+          b200rt_nif_desc nd{};
+          nd.embedding_dimension = nif_.embedding; nd.num_layers = (std::uint32_t)layers.size(); nd.layers = layers.data();
+          nd.max = nif_.max; std::copy(nif_.mean, nif_.mean + 3, nd.mean); nd.log_tone_map = (std::int32_t)nif_.logToneMap;
+          if (b200rt_scene_load_nif(sc, &nd) != 0) errors[r] = b200rt_last_error();
+          b200rt_scene_set_hdri_rotation(sc, hdriRotationDegrees_);
+          b200rt_scene_set_max_nif_batch_size(sc, nifMaxRaysPerBatch_);
+        }
+        if (errors[r].empty() && !perReplica[r].empty()) {
+          b200rt_trace_params p{};
+          p.rays_per_batch = (std::uint32_t)per;
+          CallbackCtx ctx{this, r, R};
+          if (b200rt_trace(sc, &p, perReplica[r].data(), perReplica[r].size(), rayFunc_ ? &B200Scene::trampoline : nullptr,
+                           &ctx) != 0)
+            errors[r] = b200rt_last_error();
+          b200rt_get_trace_stats(sc, &stats[r]);
+        }
+        b200rt_scene_destroy(sc);
+      });
+    }
+    for (auto& t : threads) t.join();
+    traceTimeSecs_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (auto& e : errors)
+      if (!e.empty()) throw std::runtime_error(e);
+
+    // un-batch into the caller's stream (src/IpuScene.cpp:715-732)
+    std::vector<std::size_t> cursor(R, 0);
+    for (std::size_t b = 0; b < numBatches; ++b) {
+      const std::size_t r = b % R, n = rayBatches_[b].size();
+      std::copy(perReplica[r].begin() + (long)cursor[r], perReplica[r].begin() + (long)(cursor[r] + n),
+                rayBatches_[b].begin());
+      std::copy(rayBatches_[b].begin(), rayBatches_[b].end(), rayStream_.begin() + (long)(b * per));
+      cursor[r] += n;
+    }
+    stats_ = b200rt_trace_stats{};
+    for (auto& s : stats) {
+      stats_.closest_hit_queries += s.closest_hit_queries; stats_.occlusion_queries += s.occlusion_queries;
+      stats_.samples += s.samples; stats_.escaped_samples += s.escaped_samples;
+      stats_.kernel_launches += s.kernel_launches;
+      stats_.kernel_ms = std::max(stats_.kernel_ms, s.kernel_ms);
+    }
+  }
+
+  const std::vector<SphereData>& spheres_;
+  const std::vector<DiscData>& discs_;
+  SceneRef data_;
+  std::vector<TraceResult>& rayStream_;
+  RayCallbackFn* rayFunc_;
+  std::size_t maxRaysPerWorker_;
+  RuntimeConfig config_;
+  NifWeightsFile nif_;
+  bool haveNif_ = false;
+  float hdriRotationDegrees_ = 0.f;
+  std::size_t nifMaxRaysPerBatch_ = 0;
+  double traceTimeSecs_ = 0.0;
+  b200rt_trace_stats stats_{};
+  std::vector<std::vector<TraceResult>> rayBatches_;
+};
+
+}  // namespace b200rt

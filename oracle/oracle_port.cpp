@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <vector>
 
 namespace {
@@ -532,7 +533,25 @@ inline void st3(float* p, F3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 // NIF forward on the CPU: encode (src/neural_networks/NifModel.cpp:186-219, host twin :417-433),
 // Dense layers with the auto-detected concat (:296-327), decode (:222-246 / :493-510).
 // Numerics mirror the B200 kernel's contract: fp16 features/weights/layer outputs, fp32 accumulation.
-void nifForward(const b200rt_nif_desc& nif, float u, float v, float out[3]) {
+// Weights widened to fp32 once per call (exact), so the per-sample loop is a plain fp32 GEMV.
+struct NifHost {
+  const b200rt_nif_desc& d;
+  std::vector<std::vector<float>> w, b;
+  explicit NifHost(const b200rt_nif_desc& nif) : d(nif), w(nif.num_layers), b(nif.num_layers) {
+    for (uint32_t l = 0; l < nif.num_layers; ++l) {
+      const b200rt_nif_layer& L = nif.layers[l];
+      w[l].resize((size_t)L.in_features * L.out_features);
+      for (size_t i = 0; i < w[l].size(); ++i) w[l][i] = halfToFloat(L.kernel_f16[i]);
+      if (L.bias_f16) {
+        b[l].resize(L.out_features);
+        for (uint32_t i = 0; i < L.out_features; ++i) b[l][i] = halfToFloat(L.bias_f16[i]);
+      }
+    }
+  }
+};
+
+void nifForward(const NifHost& host, float u, float v, float out[3]) {
+  const b200rt_nif_desc& nif = host.d;
   const int E = (int)nif.embedding_dimension, F = 4 * E;
   std::vector<float> feat((size_t)F);
   const float un = (u - 1.f) * 2.f, vn = (v - 1.f) * 2.f;
@@ -550,10 +569,16 @@ void nifForward(const b200rt_nif_desc& nif, float u, float v, float out[3]) {
     const b200rt_nif_layer& L = nif.layers[l];
     if (x.size() != L.in_features) x.insert(x.end(), feat.begin(), feat.end());  // concat(x, input), :303-309
     y.assign(L.out_features, 0.f);
+    const float* W = host.w[l].data();
+    // y[n] = sum_k x[k] * W[k][n], k ascending for every n (loop order chosen so the compiler vectorises over n)
+    for (uint32_t k = 0; k < L.in_features; ++k) {
+      const float xk = x[k];
+      const float* row = W + (size_t)k * L.out_features;
+      for (uint32_t n = 0; n < L.out_features; ++n) y[n] += xk * row[n];
+    }
     for (uint32_t n = 0; n < L.out_features; ++n) {
-      float acc = 0.f;
-      for (uint32_t k = 0; k < L.in_features; ++k) acc += x[k] * halfToFloat(L.kernel_f16[(size_t)k * L.out_features + n]);
-      if (L.bias_f16) acc += halfToFloat(L.bias_f16[n]);
+      float acc = y[n];
+      if (L.bias_f16) acc += host.b[l][n];
       if (L.relu) acc = acc > 0.f ? acc : 0.f;
       y[n] = halfToFloat(floatToHalf(acc));
     }
@@ -641,6 +666,8 @@ int orc_path_trace(const b200rt_scene_desc* d, void* raysV, size_t n, uint32_t f
   const uint64_t key = splitmix64(d->rng_seed);
   const uint32_t imgW = (uint32_t)d->image_width;
   const float rotation = (hdriRotationDegrees / 360.f) * (float)(2.0 * M_PI);  // src/IpuScene.cpp:641
+  std::unique_ptr<NifHost> nifHost;
+  if (nif) nifHost.reset(new NifHost(*nif));
 #pragma omp parallel num_threads(threadsOr(threads))
   {
     Counters cnt;
@@ -712,7 +739,7 @@ int orc_path_trace(const b200rt_scene_desc* d, void* raysV, size_t n, uint32_t f
           if (nif) {  // PreProcess -> NIF -> PostProcessEscapedRays
             float u, v, bgr[3];
             dirToUv(dir, rotation, u, v);
-            nifForward(*nif, u, v, bgr);
+            nifForward(*nifHost, u, v, bgr);
             rgb = add(rgb, mul(thr, f3(bgr[2], bgr[1], bgr[0])));
           }
         }
@@ -811,8 +838,9 @@ void orc_camera_sample(uint64_t rngSeed, uint32_t w, uint32_t h, float fov, floa
   }
 }
 int orc_nif_eval(const b200rt_nif_desc* nif, const float* uv, size_t n, float* out, int threads) {
+  const NifHost host(*nif);
 #pragma omp parallel for schedule(static) num_threads(threadsOr(threads))
-  for (long long i = 0; i < (long long)n; ++i) nifForward(*nif, uv[2 * i], uv[2 * i + 1], out + 3 * i);
+  for (long long i = 0; i < (long long)n; ++i) nifForward(host, uv[2 * i], uv[2 * i + 1], out + 3 * i);
   return 0;
 }
 void orc_dir_to_uv(const float* dirs, size_t n, float rotation, float* out) {

@@ -1,0 +1,288 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle. Bit-exact: integer, index and fp32 alike."""
+import numpy as np
+import pytest
+
+from conftest import assert_streams_identical
+from helpers import CustomScene, make_rays
+from ipu_ray_lib_b200 import _capi as capi, scene
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [(1, 1), (1, 2), (2, 1), (2, 2)]  # (traversal, scene_residency)
+
+
+@pytest.fixture(scope="module")
+def B200Scene():
+    from ipu_ray_lib_b200.render import B200Scene as cls
+
+    assert capi.lib().b200rt_device_count() >= 1, "no B200 visible"
+    return cls
+
+
+@pytest.mark.parametrize("name,w,h", [("box", 320, 240), ("spheres", 256, 256), ("box-simple", 200, 200)])
+def test_shadow_trace_bit_exact_all_variants(B200Scene, port, name, w, h):
+    s = scene.HostScene.builtin(name).configure(w, h, path_trace=False)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    cw = port.shadow_trace(s, want)
+    with B200Scene(s) as g:
+        for trav, res in VARIANTS:
+            got = base.copy()
+            g.execute(got, traversal=trav, scene_residency=res, count_visits=1)
+            assert_streams_identical(got, want, f"{name} shadow trav={trav} res={res}")
+            st = g.stats()
+            assert st["closest_hit_queries"] == cw["closest_hit_queries"] == w * h
+            assert st["occlusion_queries"] == cw["occlusion_queries"]
+            if trav == 1:  # same visiting order as the reference: identical work counters
+                assert st["node_visits"] == cw["node_visits"] and st["prim_tests"] == cw["prim_tests"]
+            assert st["kernel_launches"] == 1
+
+
+@pytest.mark.parametrize("name", ["box", "spheres"])
+def test_path_trace_bit_exact_all_variants(B200Scene, port, name):
+    w, h, spp = 96, 80, 9
+    s = scene.HostScene.builtin(name).configure(w, h, path_trace=True, samples=spp, seed=4242)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    cw = port.path_trace(s, want)
+    with B200Scene(s) as g:
+        for trav, res in VARIANTS:
+            got = base.copy()
+            g.execute(got, traversal=trav, scene_residency=res, count_visits=1)
+            assert_streams_identical(got, want, f"{name} path trav={trav} res={res}")
+            st = g.stats()
+            for k in ("closest_hit_queries", "samples", "escaped_samples"):
+                assert st[k] == cw[k], k
+            if trav == 1:
+                assert st["node_visits"] == cw["node_visits"] and st["prim_tests"] == cw["prim_tests"]
+
+
+def test_against_reference_build_when_present(B200Scene, ref):
+    """Same comparison against the reference's own compiled kernels (oracle/_ref)."""
+    s = scene.HostScene.builtin("box").configure(256, 256, path_trace=False)
+    base = scene.init_ray_stream(256, 256, s.fov)
+    want = base.copy()
+    ref.shadow_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got)
+        assert_streams_identical(got, want, "shadow vs reference build")
+    s.configure(64, 64, path_trace=True, samples=6)
+    base = scene.init_ray_stream(64, 64, s.fov)
+    want = base.copy()
+    ref.path_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got)
+        assert_streams_identical(got, want, "path vs reference build")
+
+
+def test_golden_fixtures_on_gpu(B200Scene, golden):
+    for name, (w, h) in {"box": (40, 40), "spheres": (32, 32)}.items():
+        s = scene.HostScene.builtin(name).configure(w, h, path_trace=False)
+        with B200Scene(s) as g:
+            rays = scene.init_ray_stream(w, h, s.fov)
+            g.execute(rays)
+            assert_streams_identical(rays, golden[f"{name}_shadow"].view(capi.TRACE_RESULT), f"{name} golden shadow")
+            q = golden[f"{name}_query_rays"].view(capi.RAY)
+            for trav in (1, 2):
+                assert g.intersect(q, traversal=trav).tobytes() == golden[f"{name}_query_hits"].tobytes()
+            assert np.array_equal(g.occluded(q), golden[f"{name}_query_occluded"])
+        s.configure(w, h, path_trace=True, samples=5)
+        with B200Scene(s) as g:
+            rays = scene.init_ray_stream(w, h, s.fov)
+            g.execute(rays)
+            assert_streams_identical(rays, golden[f"{name}_path"].view(capi.TRACE_RESULT), f"{name} golden path")
+
+
+def test_full_size_config1_shadow_trace(B200Scene, port):
+    """BASELINE config 1: built-in scene, shadow-trace, 1440x1440 — every one of the 2 073 600 rays bit-exact."""
+    w = h = 1440
+    s = scene.HostScene.builtin("box").configure(w, h, path_trace=False)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    cw = port.shadow_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got)
+        assert_streams_identical(got, want, "config 1")
+        st = g.stats()
+        assert st["closest_hit_queries"] + st["occlusion_queries"] == cw["closest_hit_queries"] + cw["occlusion_queries"]
+    hit = got["h"]["geomID"] != 0xFFFF
+    assert abs(hit.mean() - 0.693) < 0.01  # 69.3 % of primary rays hit
+    # AOVs derived from the stream are therefore identical too (normal / tfar / id images)
+    for mode in ("normal", "tfar", "id", "hitpoint", "color", "rgb"):
+        a, _ = scene.visualise_hits(got, s, mode, w, h)
+        b, _ = scene.visualise_hits(want, s, mode, w, h)
+        assert a.tobytes() == b.tobytes()
+
+
+def test_random_and_degenerate_queries(B200Scene, port, box_scene, spheres_scene):
+    rng = np.random.default_rng(11)
+    for s, lo, hi in ((box_scene, (-300, -300, -1400), (300, 300, -700)), (spheres_scene, (-4, -2, -8), (4, 3, 0))):
+        n = 200_000
+        o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+        d = rng.standard_normal((n, 3)).astype(np.float32)
+        d[::11, 0] = 0.0; d[5::13, 1] = 0.0; d[7::17, 2] = -0.0   # axis-parallel components: inf / NaN slab math
+        d[::101] = (0, 0, -1); d[3::103] = (1, 0, 0)
+        d[::2] /= np.linalg.norm(d[::2], axis=1, keepdims=True)     # half of them un-normalised
+        rays = make_rays(o, d)
+        rays["tMax"][::5] = rng.uniform(1, 900, rays["tMax"][::5].size).astype(np.float32)
+        rays["tMin"][::9] = 0.5
+        want, cw = port.intersect(s, rays)
+        with B200Scene(s) as g:
+            for trav in (1, 2):
+                got = g.intersect(rays, traversal=trav)
+                same = got.tobytes() == want.tobytes()
+                if not same:
+                    bad = np.nonzero((got.view(np.uint32).reshape(n, 6) != want.view(np.uint32).reshape(n, 6)).any(1))[0]
+                    raise AssertionError(f"trav={trav}: {bad.size} of {n} queries differ, first {bad[:5]}: {got[bad[0]]} vs {want[bad[0]]}")
+                if trav == 1:
+                    st = g.stats()
+                    assert st["node_visits"] == cw["node_visits"] and st["prim_tests"] == cw["prim_tests"]
+            assert np.array_equal(g.occluded(rays), port.occluded(s, rays))
+
+
+def test_primitive_edge_cases(B200Scene, port):
+    """Quirks the reference has and the GPU must share."""
+    tri_v = [(-1, -1, -3), (1, -1, -3), (0, 1, -3), (2, 1, -3)]
+    s = CustomScene(meshes=[(tri_v, [(0, 1, 2), (1, 3, 2)])], spheres=[(0, 0, -8, 1.5), (5, 0, -5, 1)],
+                    discs=[(0, 0, 1, 2.0, 0, 0, -12), (1, 0, 0, 1.0, -4, 0, -5)])
+    o, d = [], []
+    # shared edge / shared vertex of the two triangles, exact vertex hits
+    for x, y in ((0.5, 0.0), (1, -1), (0, 1), (0.25, 0.5), (0.75, 0.5), (1.0, 0.0)):
+        o.append((0, 0, 0)); d.append((x, y, -3))
+    # ray starting inside a sphere going forward / backward (tca < 0 rejection), tangent ray, behind the origin
+    o += [(0, 0, -8), (0, 0, -8), (1.5, 0, 0), (0, 0, -20)]
+    d += [(0, 0, -1), (0, 0, 1), (0, 0, -1), (0, 0, -1)]
+    # disc: grazing (angle == 0), hit on the rim, the abs(c.n) offset quirk with c.n > 0 (disc 1: c.n = -4 -> ok; disc 0: c.n = -12)
+    o += [(0, 0, -12), (1.999, 0, 0), (2.0, 0, 0), (-8, 0, -5), (8, 0, -5)]
+    d += [(1, 0, 0), (0, 0, -1), (0, 0, -1), (1, 0, 0), (-1, 0, 0)]
+    # direction with a zero / dominant-positive component (RayShearParams picks the signed minimum as "z")
+    o += [(0, 0, 3), (0.2, 0.1, -6), (0.2, 0.1, -6)]
+    d += [(0, 0, -1), (0, 0, 1), (0.01, 0.02, 1)]
+    rays = make_rays(o, d)
+    want, _ = port.intersect(s, rays)
+    with B200Scene(s) as g:
+        for trav in (1, 2):
+            assert g.intersect(rays, traversal=trav).tobytes() == want.tobytes()
+        assert np.array_equal(g.occluded(rays), port.occluded(s, rays))
+    assert (want["geom_id"] != 0xFFFF).sum() >= 8  # the cases do hit things
+
+
+def test_interpolated_normals_path(B200Scene, port):
+    """--load-normals: meshes with one normal per vertex use barycentric interpolation (Mesh.hpp:106-121)."""
+    rng = np.random.default_rng(5)
+    # a bumpy height-field mesh
+    n = 24
+    xs, ys = np.meshgrid(np.linspace(-3, 3, n), np.linspace(-3, 3, n))
+    zs = -6 + 0.4 * np.sin(xs * 2) * np.cos(ys * 3)
+    v = np.stack([xs, ys, zs], -1).reshape(-1, 3)
+    t = []
+    for r in range(n - 1):
+        for c in range(n - 1):
+            i = r * n + c
+            t += [(i, i + 1, i + n), (i + 1, i + n + 1, i + n)]
+    s = CustomScene(meshes=[(v, t)], normals=True).configure(120, 120, path_trace=False)
+    assert s.desc.num_normals == s.desc.num_verts
+    base = scene.init_ray_stream(120, 120, s.fov)
+    want = base.copy()
+    port.shadow_trace(s, want, light=(2.0, 5.0, 1.0), ambient=0.1)
+    with B200Scene(s) as g:
+        for trav, res in VARIANTS:
+            got = base.copy()
+            g.execute(got, traversal=trav, scene_residency=res, light_pos=(2.0, 5.0, 1.0), ambient=0.1)
+            assert_streams_identical(got, want, f"normals trav={trav} res={res}")
+    assert (want["h"]["geomID"] != 0xFFFF).mean() > 0.3
+    s.configure(64, 64, path_trace=True, samples=4)
+    base = scene.init_ray_stream(64, 64, s.fov)
+    want = base.copy()
+    port.path_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got)
+        assert_streams_identical(got, want, "normals path-trace")
+
+
+def test_empty_ragged_and_tiny_streams(B200Scene, port, box_scene):
+    s = box_scene.configure(64, 64, path_trace=False)
+    full = scene.init_ray_stream(64, 64, s.fov)
+    with B200Scene(s) as g:
+        empty = full[:0].copy()
+        g.execute(empty)  # no rays: no-op, no error
+        for n in (1, 31, 33, 127, 1000):  # not multiples of the warp size
+            got, want = full[:n].copy(), full[:n].copy()
+            g.execute(got)
+            port.shadow_trace(s, want)
+            assert_streams_identical(got, want, f"n={n}")
+
+
+def test_sample_ranges_compose_and_crop_is_consistent(B200Scene, port, box_scene):
+    """Per-(pixel,sample) RNG streams: splitting the sample range or rendering a crop window gives the same bits."""
+    w, h = 72, 56
+    s = box_scene.configure(w, h, path_trace=True, samples=10, seed=77)
+    base = scene.init_ray_stream(w, h, s.fov)
+    with B200Scene(s) as g:
+        whole = base.copy()
+        g.execute(whole)
+        parts = base.copy()
+        g.execute(parts, first_sample=0, num_samples=3)
+        g.execute(parts, first_sample=3, num_samples=6)
+        g.execute(parts, first_sample=9, num_samples=1)
+        assert_streams_identical(parts, whole, "sample ranges")
+        crop = scene.init_ray_stream(w, h, s.fov, window=(24, 16, 30, 20))
+        g.execute(crop)
+        sel = whole.reshape(h, w)[20:36, 30:54].ravel()
+        assert_streams_identical(crop, sel, "crop window")
+    want = base.copy()
+    port.path_trace(s, want)
+    assert_streams_identical(whole, want, "whole vs oracle")
+
+
+def test_callback_batches_cover_the_stream_in_order(B200Scene, port, spheres_scene):
+    s = spheres_scene.configure(100, 70, path_trace=False)
+    base = scene.init_ray_stream(100, 70, s.fov)
+    want = base.copy()
+    port.shadow_trace(s, want)
+    seen = []
+
+    def cb(idx, batch):
+        seen.append((idx, batch.copy()))
+
+    with B200Scene(s, ray_callback=cb) as g:
+        got = base.copy()
+        g.execute(got, rays_per_batch=1536)
+    assert [i for i, _ in seen] == list(range((7000 + 1535) // 1536))
+    assert_streams_identical(np.concatenate([b for _, b in seen]), want, "callback batches")
+    assert_streams_identical(got, want, "in-place result")
+
+
+def test_device_resident_entry_point(B200Scene, port, box_scene):
+    torch = pytest.importorskip("torch")
+    w, h = 128, 128
+    s = box_scene.configure(w, h, path_trace=True, samples=4)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    port.path_trace(s, want)
+    d = torch.from_numpy(base.view(np.uint8).copy()).cuda()
+    with B200Scene(s) as g:
+        g.execute_device(d.data_ptr(), base.size)
+        st = g.stats()
+    got = d.cpu().numpy().view(capi.TRACE_RESULT)
+    assert_streams_identical(got, want, "device-resident")
+    assert st["h2d_ms"] == 0 and st["d2h_ms"] == 0 and st["kernel_ms"] > 0
+
+
+def test_error_flag_on_unknown_material(B200Scene, port):
+    mats = np.zeros(1, capi.MATERIAL)
+    mats["albedo"] = 0.5
+    mats["type"] = 7  # not Diffuse/Specular/Refractive: rgb *= NaN, flags |= ERROR (trace.cpp:166-170)
+    s = CustomScene(spheres=[(0, 0, -5, 1.5)], materials=mats).configure(32, 32, path_trace=True, samples=2)
+    base = scene.init_ray_stream(32, 32, s.fov)
+    want = base.copy()
+    port.path_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got)
+    assert_streams_identical(got, want, "error flag")
+    assert (got["h"]["flags"] & 1).any()
