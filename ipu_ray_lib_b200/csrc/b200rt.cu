@@ -583,7 +583,9 @@ int b200rt_intersect(b200rt_scene* sc, const void* raysIn, size_t n, b200rt_hit*
   CU_TRY(dH.reserve(n * sizeof(rt::QueryHit)));
   CU_TRY(cudaMemsetAsync(sc->counters.p, 0, sizeof(rt::DeviceCounters), sc->stream));
   const uint32_t threads = 128, blocks = (uint32_t)((n + threads - 1) / threads);
-  if (traversal == 1)
+  // Bare queries may carry non-unit directions, for which only the reference's own visiting order is
+  // guaranteed to reproduce its answers (see DESIGN.md "Traversal order"): auto = reference order here.
+  if (traversal != 2)
     rt::intersect_kernel<false><<<blocks, threads, 0, sc->stream>>>(sc->dev, (const float*)dR.p, (uint32_t)n,
                                                                    (rt::QueryHit*)dH.p, (rt::DeviceCounters*)sc->counters.p);
   else

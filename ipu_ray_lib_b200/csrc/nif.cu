@@ -16,8 +16,12 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
+
+#include "nif_tc.cuh"
 
 namespace rt {
 
@@ -50,7 +54,100 @@ struct NifModel {
   NifParams p{};
   std::vector<void*> allocs;
   int device = 0;
+  // tensor-core path
+  bool tcOk = false;
+  tc::Params tc{};
+  size_t tcSmem = 0;
+  std::string tcWhyNot;
 };
+
+namespace {
+
+// Builds the B-operand images W[k/8][n][k%8] (fp16, N padded to 16 with zeros) and fp32 biases for the
+// tcgen05 kernel. Returns false (with a reason) when the model does not fit its tiling rules.
+bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
+  auto no = [&](const std::string& why) { m->tcWhyNot = why; return false; };
+  const int E = (int)d.embedding_dimension, F = 4 * E;
+  if (F % 16 != 0) return no("feature width 4E is not a multiple of 16");
+  tc::Params& t = m->tc;
+  t = tc::Params{};
+  t.numLayers = (int)d.num_layers;
+  t.embed = E;
+  int maxHidden = 0;
+  for (uint32_t i = 0; i + 1 < d.num_layers; ++i) maxHidden = std::max(maxHidden, (int)d.layers[i].out_features);
+  if (maxHidden % 16 != 0) return no("hidden width is not a multiple of 16");
+  t.featCol = maxHidden;
+  int width = F, maxNpad = 16, biasFloats = 0, xCols = maxHidden + F;
+  for (uint32_t i = 0; i < d.num_layers; ++i) {
+    const b200rt_nif_layer& L = d.layers[i];
+    tc::Layer& o = t.layers[i];
+    o.K = (int)L.in_features; o.N = (int)L.out_features; o.Npad = (o.N + 15) / 16 * 16; o.relu = L.relu;
+    const bool last = i + 1 == d.num_layers;
+    if (o.K % 16 != 0) return no("layer K is not a multiple of 16");
+    if (!last && o.N % 16 != 0) return no("hidden width is not a multiple of 16");
+    if (o.Npad > 512) return no("layer wider than the 512 TMEM columns");
+    o.copyFeatTo = -1;
+    if (i == 0) {
+      if (o.K != F) return no("first layer does not take the encoded input");
+      o.aPlane0 = t.featCol / 8;
+    } else {
+      o.aPlane0 = 0;
+      if (o.K == width + F) {            // skip-concat (NifModel.cpp:303-309)
+        if (width != t.featCol) o.copyFeatTo = width;
+        xCols = std::max(xCols, width + F);
+      } else if (o.K != width) {
+        return no("layer input width mismatch");
+      }
+    }
+    width = o.N;
+    maxNpad = std::max(maxNpad, o.Npad);
+    biasFloats += o.Npad;
+  }
+  if (width != 3) return no("last layer must have 3 outputs");
+  t.xPlanes = (xCols + 7) / 8;
+  t.stageBytes = (tc::kStageK / 8) * maxNpad * 16;
+  t.biasFloats = biasFloats;
+  t.maxv = d.max; t.mean0 = d.mean[0]; t.mean1 = d.mean[1]; t.mean2 = d.mean[2];
+  t.logToneMap = d.log_tone_map;
+  const char* sw = std::getenv("B200RT_NIF_SWAP_LBO_SBO");
+  t.swapLboSbo = (sw && sw[0] == '1') ? 1 : 0;
+  m->tcSmem = (size_t)t.xPlanes * tc::kPlaneBytes + (size_t)tc::kStages * t.stageBytes +
+              (size_t)((biasFloats + 1) & ~1) * 4 + (2 * tc::kStages + 2) * 8 + 16;
+  int maxSmem = 0;
+  cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
+  if (m->tcSmem > (size_t)maxSmem) return no("activation tile + weight ring exceed shared memory");
+
+  for (uint32_t i = 0; i < d.num_layers; ++i) {
+    const b200rt_nif_layer& L = d.layers[i];
+    tc::Layer& o = t.layers[i];
+    std::vector<__half> img((size_t)o.K * o.Npad, __float2half(0.f));
+    const __half* src = reinterpret_cast<const __half*>(L.kernel_f16);
+    for (int k = 0; k < o.K; ++k)
+      for (int n = 0; n < o.N; ++n)
+        img[((size_t)(k / 8) * o.Npad + n) * 8 + (k % 8)] = src[(size_t)k * o.N + n];
+    std::vector<float> bias((size_t)o.Npad, 0.f);
+    if (L.bias_f16)
+      for (int n = 0; n < o.N; ++n) bias[(size_t)n] = __half2float(reinterpret_cast<const __half*>(L.bias_f16)[n]);
+    void *dw = nullptr, *db = nullptr;
+    if (cudaMalloc(&dw, img.size() * 2) != cudaSuccess || cudaMalloc(&db, bias.size() * 4) != cudaSuccess) {
+      if (dw) cudaFree(dw);
+      return no("cudaMalloc failed");
+    }
+    m->allocs.push_back(dw);
+    m->allocs.push_back(db);
+    cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
+    o.wimg = (const __half*)dw;
+    o.bias = (const float*)db;
+  }
+  if (cudaFuncSetAttribute(tc::nif_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tcSmem) != cudaSuccess) {
+    cudaGetLastError();
+    return no("cudaFuncSetAttribute(max dynamic shared memory) failed");
+  }
+  return true;
+}
+
+}  // namespace
 
 const char* nif_last_error() { return g_nifError.c_str(); }
 
@@ -107,6 +204,11 @@ NifModel* nif_create(const b200rt_nif_desc& d, int device) {
     }
   }
   if (width != 3) { nif_destroy(m); return bad("last NIF layer must have 3 outputs (b,g,r)"); }
+  // Tensor-core path (the product path). Models outside its tiling rules (widths not multiples of 16)
+  // run on the CUDA-core kernel below; B200RT_NIF_IMPL=simt forces that kernel for debugging.
+  m->tcOk = prepare_tc(m, d);
+  const char* impl = std::getenv("B200RT_NIF_IMPL");
+  if (impl && std::strcmp(impl, "simt") == 0) { m->tcOk = false; m->tcWhyNot = "forced by B200RT_NIF_IMPL=simt"; }
   return m;
 }
 
@@ -207,6 +309,15 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
   if (!m) { g_nifError = "no model"; return -1; }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  if (m->tcOk) {
+    const uint32_t tcTiles = (count + tc::kRows - 1) / tc::kRows;
+    const uint32_t tcGrid = tcTiles < (uint32_t)sms ? (tcTiles ? tcTiles : 1u) : (uint32_t)sms;  // one persistent CTA per SM
+    tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(m->tc, uvDirect, slotEscape, queue, dCount, count, out);
+    const cudaError_t te = cudaGetLastError();
+    if (te != cudaSuccess) { g_nifError = cudaGetErrorString(te); return -1; }
+    if (launches) *launches += 1;
+    return 0;
+  }
   const uint32_t tiles = (count + kTileRows - 1) / kTileRows;
   const uint32_t grid = tiles < (uint32_t)(sms * 4) ? (tiles ? tiles : 1u) : (uint32_t)(sms * 4);
   nif_mlp_kernel<<<grid, kThreads, 0, stream>>>(m->p, uvDirect, slotEscape, queue, dCount, count, out);

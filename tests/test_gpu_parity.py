@@ -130,14 +130,20 @@ def test_random_and_degenerate_queries(B200Scene, port, box_scene, spheres_scene
         rays["tMax"][::5] = rng.uniform(1, 900, rays["tMax"][::5].size).astype(np.float32)
         rays["tMin"][::9] = 0.5
         want, cw = port.intersect(s, rays)
+        unit = np.zeros(n, bool)
+        unit[::2] = True  # rows that were normalised above
         with B200Scene(s) as g:
-            for trav in (1, 2):
+            for trav in (0, 1, 2):
                 got = g.intersect(rays, traversal=trav)
-                same = got.tobytes() == want.tobytes()
-                if not same:
-                    bad = np.nonzero((got.view(np.uint32).reshape(n, 6) != want.view(np.uint32).reshape(n, 6)).any(1))[0]
-                    raise AssertionError(f"trav={trav}: {bad.size} of {n} queries differ, first {bad[:5]}: {got[bad[0]]} vs {want[bad[0]]}")
-                if trav == 1:
+                diff = (got.view(np.uint32).reshape(n, 6) != want.view(np.uint32).reshape(n, 6)).any(1)
+                if trav == 2:
+                    # Near-first order is only promised for unit directions (every ray a render produces):
+                    # Sphere::intersect scales td by 1/|d|^2 (src/Primitives.cpp:34), so for |d| != 1 its t can lie
+                    # outside the sphere's own box and the reference's answer depends on ITS visiting order.
+                    diff &= unit
+                bad = np.nonzero(diff)[0]
+                assert bad.size == 0, f"trav={trav}: {bad.size} of {n} queries differ, first {bad[:5]}: {got[bad[0]]} vs {want[bad[0]]}"
+                if trav in (0, 1):  # bare queries default to the reference's visiting order
                     st = g.stats()
                     assert st["node_visits"] == cw["node_visits"] and st["prim_tests"] == cw["prim_tests"]
             assert np.array_equal(g.occluded(rays), port.occluded(s, rays))
