@@ -63,56 +63,52 @@ struct NifModel {
 
 namespace {
 
-// Builds the B-operand images W[k/8][n][k%8] (fp16, N padded to 16 with zeros) and fp32 biases for the
-// tcgen05 kernel. Returns false (with a reason) when the model does not fit its tiling rules.
+// Builds the B-operand images W[k/8][n][k%8] (fp16, N padded to 16 with zeros) for the tcgen05 kernel. The K order
+// of an image is [rows multiplying the previous activations | bias row + 15 zero rows (the "ones" slice) | rows
+// multiplying the encoded input], matching the A-operand slices the kernel walks. Returns false (with a reason)
+// when the model does not fit the kernel's tiling rules.
 bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
   auto no = [&](const std::string& why) { m->tcWhyNot = why; return false; };
   const int E = (int)d.embedding_dimension, F = 4 * E;
   if (F % 16 != 0) return no("feature width 4E is not a multiple of 16");
+  if (2 + F / 8 > tc::kStaticPlanesMax) return no("encoded input wider than the static region");
   tc::Params& t = m->tc;
   t = tc::Params{};
   t.numLayers = (int)d.num_layers;
   t.embed = E;
-  int maxHidden = 0;
-  for (uint32_t i = 0; i + 1 < d.num_layers; ++i) maxHidden = std::max(maxHidden, (int)d.layers[i].out_features);
-  if (maxHidden % 16 != 0) return no("hidden width is not a multiple of 16");
-  t.featCol = maxHidden;
-  int width = F, maxNpad = 16, biasFloats = 0, xCols = maxHidden + F;
+  int width = F, maxNpad = 16, maxHidden = 16;
+  std::vector<int> actRows(d.num_layers), featRows(d.num_layers);
   for (uint32_t i = 0; i < d.num_layers; ++i) {
     const b200rt_nif_layer& L = d.layers[i];
     tc::Layer& o = t.layers[i];
-    o.K = (int)L.in_features; o.N = (int)L.out_features; o.Npad = (o.N + 15) / 16 * 16; o.relu = L.relu;
+    const int K = (int)L.in_features;
+    o.N = (int)L.out_features; o.Npad = (o.N + 15) / 16 * 16; o.relu = L.relu;
     const bool last = i + 1 == d.num_layers;
-    if (o.K % 16 != 0) return no("layer K is not a multiple of 16");
     if (!last && o.N % 16 != 0) return no("hidden width is not a multiple of 16");
     if (o.Npad > 512) return no("layer wider than the 512 TMEM columns");
-    o.copyFeatTo = -1;
     if (i == 0) {
-      if (o.K != F) return no("first layer does not take the encoded input");
-      o.aPlane0 = t.featCol / 8;
+      if (K != F) return no("first layer does not take the encoded input");
+      actRows[i] = 0; featRows[i] = F;
+    } else if (K == width + F) {  // skip-concat (NifModel.cpp:303-309)
+      actRows[i] = width; featRows[i] = F;
+    } else if (K == width) {
+      actRows[i] = width; featRows[i] = 0;
     } else {
-      o.aPlane0 = 0;
-      if (o.K == width + F) {            // skip-concat (NifModel.cpp:303-309)
-        if (width != t.featCol) o.copyFeatTo = width;
-        xCols = std::max(xCols, width + F);
-      } else if (o.K != width) {
-        return no("layer input width mismatch");
-      }
+      return no("layer input width mismatch");
     }
+    o.actSlices = actRows[i] / 16;
+    o.staticSlices = 1 + featRows[i] / 16;
     width = o.N;
     maxNpad = std::max(maxNpad, o.Npad);
-    biasFloats += o.Npad;
+    if (!last) maxHidden = std::max(maxHidden, o.N);
   }
   if (width != 3) return no("last layer must have 3 outputs");
-  t.xPlanes = (xCols + 7) / 8;
+  t.actPlanes = maxHidden / 8;
   t.stageBytes = (tc::kStageK / 8) * maxNpad * 16;
-  t.biasFloats = biasFloats;
   t.maxv = d.max; t.mean0 = d.mean[0]; t.mean1 = d.mean[1]; t.mean2 = d.mean[2];
   t.logToneMap = d.log_tone_map;
-  const char* sw = std::getenv("B200RT_NIF_SWAP_LBO_SBO");
-  t.swapLboSbo = (sw && sw[0] == '1') ? 1 : 0;
-  m->tcSmem = (size_t)t.xPlanes * tc::kPlaneBytes + (size_t)tc::kStages * t.stageBytes +
-              (size_t)((biasFloats + 1) & ~1) * 4 + (2 * tc::kStages + 2) * 8 + 16;
+  m->tcSmem = (size_t)(t.actPlanes + tc::kStaticPlanesMax) * tc::kPlaneBytes + (size_t)tc::kStages * t.stageBytes +
+              (2 * tc::kStages + 2) * 8 + 16;
   int maxSmem = 0;
   cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
   if (m->tcSmem > (size_t)maxSmem) return no("activation tile + weight ring exceed shared memory");
@@ -120,25 +116,20 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
   for (uint32_t i = 0; i < d.num_layers; ++i) {
     const b200rt_nif_layer& L = d.layers[i];
     tc::Layer& o = t.layers[i];
-    std::vector<__half> img((size_t)o.K * o.Npad, __float2half(0.f));
+    const int Keff = 16 * (o.actSlices + o.staticSlices);
+    std::vector<__half> img((size_t)Keff * o.Npad, __float2half(0.f));
     const __half* src = reinterpret_cast<const __half*>(L.kernel_f16);
-    for (int k = 0; k < o.K; ++k)
-      for (int n = 0; n < o.N; ++n)
-        img[((size_t)(k / 8) * o.Npad + n) * 8 + (k % 8)] = src[(size_t)k * o.N + n];
-    std::vector<float> bias((size_t)o.Npad, 0.f);
-    if (L.bias_f16)
-      for (int n = 0; n < o.N; ++n) bias[(size_t)n] = __half2float(reinterpret_cast<const __half*>(L.bias_f16)[n]);
-    void *dw = nullptr, *db = nullptr;
-    if (cudaMalloc(&dw, img.size() * 2) != cudaSuccess || cudaMalloc(&db, bias.size() * 4) != cudaSuccess) {
-      if (dw) cudaFree(dw);
-      return no("cudaMalloc failed");
+    auto put = [&](int k, int n, __half v) { img[((size_t)(k / 8) * o.Npad + n) * 8 + (k % 8)] = v; };
+    for (int n = 0; n < o.N; ++n) {
+      for (int k = 0; k < actRows[i]; ++k) put(k, n, src[(size_t)k * o.N + n]);
+      if (L.bias_f16) put(actRows[i], n, reinterpret_cast<const __half*>(L.bias_f16)[n]);
+      for (int k = 0; k < featRows[i]; ++k) put(actRows[i] + 16 + k, n, src[(size_t)(actRows[i] + k) * o.N + n]);
     }
+    void* dw = nullptr;
+    if (cudaMalloc(&dw, img.size() * 2) != cudaSuccess) return no("cudaMalloc failed");
     m->allocs.push_back(dw);
-    m->allocs.push_back(db);
     cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice);
-    cudaMemcpy(db, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
     o.wimg = (const __half*)dw;
-    o.bias = (const float*)db;
   }
   if (cudaFuncSetAttribute(tc::nif_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tcSmem) != cudaSuccess) {
     cudaGetLastError();

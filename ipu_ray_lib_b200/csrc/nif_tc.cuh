@@ -4,15 +4,16 @@
 //   * activations live in shared memory as the fp16 A operand, K-major, no-swizzle "core matrix" layout
 //     X[k/8][row][k%8] (a plane of 128 rows x 16 B per 8 columns of K), so a row's 8 consecutive
 //     features are one 16-byte store and 32 lanes store 512 contiguous bytes (no bank conflicts);
-//   * weights are pre-arranged on the host into the matching B-operand image W[k/8][n][k%8] and streamed
-//     from L2 through a 3-stage ring of cp.async.bulk (TMA engine, SASS UBLKCP) copies signalled on mbarriers;
+//   * behind the activations sits a static region S = [ones | encoded input]: the "ones" slice turns every
+//     layer's bias into one more K-slice of the GEMM (no bias add in the epilogue), and the encoded input
+//     makes the skip-concat layer a plain longer K;
+//   * weights (+ bias row) are pre-arranged on the host into the matching B-operand image W[k/8][n][k%8] and
+//     streamed from L2 through a ring of cp.async.bulk (TMA engine, SASS UBLKCP) copies signalled on mbarriers;
 //   * each layer is a chain of tcgen05.mma (M=128, N<=256 per instruction, K=16, fp16 x fp16 -> fp32 in
 //     TMEM) issued by ONE thread; tcgen05.commit releases ring stages and publishes "accumulator ready";
-//   * the epilogue (4 warps, one TMEM lane quarter each) reads the accumulators with tcgen05.ld, adds the
-//     bias, applies ReLU, rounds to fp16 and writes the next layer's A operand in place; the encoded
-//     input stays parked behind the activations so the skip-concat layer is a plain longer K.
-// Roles: warps 0-3 = encode + epilogue (thread t <-> row t), warp 4 lane 0 = weight producer,
-// warp 5 lane 0 = MMA issuer.
+//   * the epilogue (8 warps: TMEM lane quarter = warp%4, column half = warp/4) reads the accumulators with
+//     tcgen05.ld, rounds to fp16, applies ReLU on packed halves and writes the next layer's A operand in place.
+// Roles: warps 0-7 = encode + epilogue, warp 8 lane 0 = weight producer, warp 9 lane 0 = MMA issuer.
 #pragma once
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -21,32 +22,30 @@ namespace rt {
 namespace tc {
 
 constexpr int kRows = 128;          // rows (escaped rays) per tile == TMEM lanes
-constexpr int kStages = 3;          // weight ring depth
-constexpr int kStageK = 64;         // K elements per ring stage (4 MMAs of K=16)
+constexpr int kStages = 4;          // weight ring depth
+constexpr int kStageK = 32;         // K elements per ring stage (2 MMA K-slices)
 constexpr int kMaxLayers = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kPlaneBytes = kRows * 16;  // one K-chunk (8 columns) of the A operand
+constexpr int kStaticPlanesMax = 2 + 8;  // ones slice (2 planes) + up to 64 encoded features
 
 struct Layer {
-  const __half* wimg;   // [K/8][Npad][8] fp16
-  const float* bias;    // [Npad] fp32
-  int K, N, Npad;       // Npad = N rounded up to 16
+  const __half* wimg;   // [Keff/8][Npad][8] fp16, K order = [activation rows | bias row + 15 zero rows | feature rows]
+  int actSlices;        // K=16 slices read from the activation planes (0 for the first layer)
+  int staticSlices;     // slices read from S: 1 (ones) or 1 + F/16 (ones + encoded input)
+  int N, Npad;          // Npad = N rounded up to 16
   int relu;
-  int aPlane0;          // first A plane this layer reads
-  int copyFeatTo;       // >= 0: before this layer, copy the parked features to this column (concat at odd width)
 };
 
 struct Params {
   Layer layers[kMaxLayers];
   int numLayers;
   int embed;            // E, features F = 4E
-  int featCol;          // column where the encoded input is parked (multiple of 8)
-  int xPlanes;          // planes in the X buffer
+  int actPlanes;        // planes of the activation buffer (max hidden width / 8)
   int stageBytes;       // bytes of one ring stage
-  int biasFloats;       // total bias floats (all layers, padded)
   float maxv, mean0, mean1, mean2;
   int logToneMap;
-  int swapLboSbo;       // debug switch: exchange the descriptor's leading/stride offsets
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -126,14 +125,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -154,25 +150,17 @@ __device__ __forceinline__ uint32_t instr_desc(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// Encode one (u,v) into 4E fp16 features, packed as 8-column chunks (src/neural_networks/NifModel.cpp:186-219).
-__device__ __forceinline__ void encode_row(float u, float v, int E, unsigned char* xRow /* X + row*16 */, int featPlane0) {
-  const float un = (u - 1.f) * 2.f, vn = (v - 1.f) * 2.f;
-  // feature index f = j (sin u), E + j (sin v), 2E + j (cos u), 3E + j (cos v)
-  float c = 1.f;
-  for (int j = 0; j < E; ++j, c *= 2.f) {
-    const float au = __half2float(__float2half_rn(un * c));
-    const float av = __half2float(__float2half_rn(vn * c));
-    float su, cu, sv, cv;
-    sincosf(au, &su, &cu);
-    sincosf(av, &sv, &cv);
-    const int f[4] = {j, E + j, 2 * E + j, 3 * E + j};
-    const float val[4] = {su, sv, cu, cv};
+// relu + round-to-fp16 of 8 fp32 accumulators -> one 16-byte chunk of the next A operand
+__device__ __forceinline__ uint4 pack8(const uint32_t* acc, bool relu) {
+  uint32_t w[4];
+  const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      __half* dst = reinterpret_cast<__half*>(xRow + (size_t)(featPlane0 + (f[q] >> 3)) * kPlaneBytes) + (f[q] & 7);
-      *dst = __float2half_rn(val[q]);
-    }
+  for (int e = 0; e < 4; ++e) {
+    __half2 h = __floats2half2_rn(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+    if (relu) h = __hmax2(h, zero);
+    w[e] = *reinterpret_cast<const uint32_t*>(&h);
   }
+  return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -181,14 +169,14 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
                   const uint32_t* __restrict__ queue, const uint32_t* __restrict__ dCount, uint32_t directCount,
                   float* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  // layout: [X planes][ring stages][bias floats][barriers][tmem ptr]
+  // layout: [activation planes][static planes: ones, encoded input][ring stages][barriers][tmem ptr]
   unsigned char* X = smem;
-  unsigned char* ring = X + (size_t)p.xPlanes * kPlaneBytes;
-  float* biasS = reinterpret_cast<float*>(ring + (size_t)kStages * p.stageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(biasS + ((p.biasFloats + 1) & ~1));
-  uint64_t* fullBar = bars;                 // [kStages] weights landed
-  uint64_t* emptyBar = bars + kStages;      // [kStages] MMAs that read the stage have completed
-  uint64_t* actBar = bars + 2 * kStages;    // A operand of the next layer is ready (128 arrivals)
+  unsigned char* S = X + (size_t)p.actPlanes * kPlaneBytes;
+  unsigned char* ring = S + (size_t)kStaticPlanesMax * kPlaneBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * p.stageBytes);
+  uint64_t* fullBar = bars;                   // [kStages] weights landed
+  uint64_t* emptyBar = bars + kStages;        // [kStages] MMAs that read the stage have completed
+  uint64_t* actBar = bars + 2 * kStages;      // A operand of the next layer is ready (256 arrivals)
   uint64_t* accBar = bars + 2 * kStages + 1;  // accumulator of the current layer is complete (1 arrival via commit)
   uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
 
@@ -198,23 +186,23 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(fullBar + s, 1); mbar_init(emptyBar + s, 1); }
-    mbar_init(actBar, kRows);
+    mbar_init(actBar, kEpiWarps * 32);
     mbar_init(accBar, 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.biasFloats; i += kThreads) {
-    // biases of all layers, concatenated in layer order
-    int l = 0, off = i;
-    while (off >= p.layers[l].Npad) { off -= p.layers[l].Npad; ++l; }
-    biasS[i] = p.layers[l].bias[off];
+  // the ones slice: column 0 = 1.0, columns 1..15 = 0 (the matching weight rows hold the bias and zeros)
+  for (int i = threadIdx.x; i < 2 * kRows * 8; i += kThreads) {
+    const int plane = i / (kRows * 8), e = i % 8;
+    reinterpret_cast<__half*>(S)[i] = __float2half((plane == 0 && e == 0) ? 1.f : 0.f);
   }
   if (warp == 0) tmem_alloc(tmemPtr, 512);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmemBase = *tmemPtr;
 
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     // ===== weight producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -222,24 +210,24 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
         for (int l = 0; l < p.numLayers; ++l) {
           const Layer& L = p.layers[l];
           const uint32_t planeBytes = (uint32_t)L.Npad * 16u;
-          const uint32_t totalPlanes = (uint32_t)L.K / 8u;
+          const uint32_t totalPlanes = 2u * (uint32_t)(L.actSlices + L.staticSlices);
           for (uint32_t pl = 0; pl < totalPlanes; pl += kStageK / 8) {
             const uint32_t planes = min((uint32_t)(kStageK / 8), totalPlanes - pl);
             const uint32_t bytes = planes * planeBytes;
             mbar_wait(emptyBar + stage, phase ^ 1u);
             mbar_expect_tx(fullBar + stage, bytes);
-            bulk_load(ring + (size_t)stage * p.stageBytes, reinterpret_cast<const unsigned char*>(L.wimg) + (size_t)pl * planeBytes,
-                      bytes, fullBar + stage);
+            bulk_load(ring + (size_t)stage * p.stageBytes,
+                      reinterpret_cast<const unsigned char*>(L.wimg) + (size_t)pl * planeBytes, bytes, fullBar + stage);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, actPhase = 0;
-      const uint32_t xAddr = smem_u32(X), ringAddr = smem_u32(ring);
+      const uint32_t xAddr = smem_u32(X), sAddr = smem_u32(S), ringAddr = smem_u32(ring);
       for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
         for (int l = 0; l < p.numLayers; ++l) {
           const Layer& L = p.layers[l];
@@ -247,21 +235,21 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
           mbar_wait(actBar, actPhase);
           actPhase ^= 1u;
           tc_fence_after();
-          const uint32_t slices = (uint32_t)L.K / 16u;
+          const uint32_t slices = (uint32_t)(L.actSlices + L.staticSlices);
           for (uint32_t ks = 0; ks < slices; ++ks) {
             const uint32_t inStage = ks % (kStageK / 16);
             if (inStage == 0) {
               mbar_wait(fullBar + stage, phase);
               tc_fence_after();
             }
-            const uint32_t aAddr = xAddr + (uint32_t)(L.aPlane0 + 2 * (int)ks) * kPlaneBytes;
+            const uint32_t aAddr = ks < (uint32_t)L.actSlices ? xAddr + 2u * ks * kPlaneBytes
+                                                              : sAddr + 2u * (ks - (uint32_t)L.actSlices) * kPlaneBytes;
             const uint32_t bAddr = ringAddr + stage * (uint32_t)p.stageBytes + inStage * 2u * planeBytesB;
-            const uint64_t aDesc = p.swapLboSbo ? smem_desc(aAddr, 128u, kPlaneBytes) : smem_desc(aAddr, kPlaneBytes, 128u);
+            const uint64_t aDesc = smem_desc(aAddr, kPlaneBytes, 128u);
             for (int n0 = 0; n0 < L.Npad; n0 += 160) {
               int nc = L.Npad - n0;
               if (nc > 160) nc = 160;  // N per instruction: multiple of 16, at most 256; 320 = 160 + 160
-              const uint32_t bA = bAddr + (uint32_t)n0 * 16u;
-              const uint64_t bDesc = p.swapLboSbo ? smem_desc(bA, 128u, planeBytesB) : smem_desc(bA, planeBytesB, 128u);
+              const uint64_t bDesc = smem_desc(bAddr + (uint32_t)n0 * 16u, planeBytesB, 128u);
               mma_f16(tmemBase + (uint32_t)n0, aDesc, bDesc, instr_desc(kRows, nc), ks > 0 ? 1u : 0u);
             }
             if (inStage == kStageK / 16 - 1 || ks == slices - 1) {
@@ -274,12 +262,14 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
       }
     }
   } else {
-    // ===== encode + epilogue: thread t owns row t (TMEM lane t) =====
-    const int row = threadIdx.x;
+    // ===== encode + epilogue: row = (warp % 4) * 32 + lane (TMEM lane), column half = warp / 4 =====
+    const int row = (warp & 3) * 32 + lane;
+    const int half = warp >> 2;
     unsigned char* xRow = X + (size_t)row * 16;
-    const uint32_t laneTaddr = tmemBase + ((uint32_t)(warp * 32) << 16);
+    unsigned char* sRow = S + (size_t)row * 16;
+    const uint32_t laneTaddr = tmemBase + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t accPhase = 0;
-    const int F = 4 * p.embed;
+    const int E = p.embed;
     for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
       const uint32_t r = tile * kRows + (uint32_t)row;
       float u = 0.f, v = 0.f;
@@ -288,11 +278,23 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
         if (uvDirect) { slot = r; u = uvDirect[2 * (size_t)r]; v = uvDirect[2 * (size_t)r + 1]; }
         else { slot = queue[r]; u = slotEscape[5 * (size_t)slot + 3]; v = slotEscape[5 * (size_t)slot + 4]; }
       }
-      encode_row(u, v, p.embed, xRow, p.featCol / 8);
+      // Encode (src/neural_networks/NifModel.cpp:186-219): half 0 does the u features, half 1 the v features.
+      // Feature order: [sin u]_E [sin v]_E [cos u]_E [cos v]_E, parked in S after the ones slice.
+      {
+        const float w = ((half == 0 ? u : v) - 1.f) * 2.f;
+        float c = 1.f;
+        for (int j = 0; j < E; ++j, c *= 2.f) {
+          const float a = __half2float(__float2half_rn(w * c));
+          float sn, cs;
+          sincosf(a, &sn, &cs);
+          const int fs = half * E + j, fc = 2 * E + half * E + j;
+          reinterpret_cast<__half*>(sRow + (size_t)(2 + (fs >> 3)) * kPlaneBytes)[fs & 7] = __float2half_rn(sn);
+          reinterpret_cast<__half*>(sRow + (size_t)(2 + (fc >> 3)) * kPlaneBytes)[fc & 7] = __float2half_rn(cs);
+        }
+      }
       fence_proxy_async();
       mbar_arrive(actBar);
 
-      int bOff = 0;
       for (int l = 0; l < p.numLayers; ++l) {
         const Layer& L = p.layers[l];
         mbar_wait(accBar, accPhase);
@@ -300,57 +302,48 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
         tc_fence_after();
         const bool last = l == p.numLayers - 1;
         if (last) {
-          uint32_t acc[32];
-          tmem_ld16(laneTaddr, acc);
-          tmem_ld_wait();
-          if (slot != 0xFFFFFFFFu) {
+          if (half == 0) {
+            uint32_t acc[8];
+            tmem_ld8(laneTaddr, acc);
+            tmem_ld_wait();
+            if (slot != 0xFFFFFFFFu) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float y = __uint_as_float(acc[c]) + biasS[bOff + c];
-              if (L.relu) y = y > 0.f ? y : 0.f;
-              y = __half2float(__float2half_rn(y));  // layer outputs are fp16 (NifModel.cpp:313-315)
-              const float mean = c == 0 ? p.mean0 : (c == 1 ? p.mean1 : p.mean2);
-              y = y * p.maxv + mean;                  // decode (NifModel.cpp:222-246)
-              if (p.logToneMap) y = expf(y);
-              out[3 * (size_t)slot + c] = y;
+              for (int c = 0; c < 3; ++c) {
+                float y = __uint_as_float(acc[c]);
+                if (L.relu) y = y > 0.f ? y : 0.f;
+                y = __half2float(__float2half_rn(y));  // layer outputs are fp16 (NifModel.cpp:313-315)
+                const float mean = c == 0 ? p.mean0 : (c == 1 ? p.mean1 : p.mean2);
+                y = y * p.maxv + mean;                  // decode (NifModel.cpp:222-246)
+                if (p.logToneMap) y = expf(y);
+                out[3 * (size_t)slot + c] = y;
+              }
             }
           }
           tc_fence_before();
         } else {
-          for (int c0 = 0; c0 < L.Npad; c0 += 32) {
+          // this thread's columns: [c0, c1); the two halves split Npad when it is a multiple of 64
+          const bool split = (L.Npad & 63) == 0;
+          const int c0 = split ? half * (L.Npad >> 1) : 0;
+          const int c1 = split ? c0 + (L.Npad >> 1) : (half == 0 ? L.Npad : 0);
+          int c = c0;
+          for (; c + 32 <= c1; c += 32) {
             uint32_t acc[32];
-            const bool full = c0 + 32 <= L.Npad;
-            if (full) tmem_ld32(laneTaddr + (uint32_t)c0, acc); else tmem_ld16(laneTaddr + (uint32_t)c0, acc);
+            tmem_ld32(laneTaddr + (uint32_t)c, acc);
             tmem_ld_wait();
-            const int cols = full ? 32 : 16;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < cols) {
-                uint32_t packed[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float y0 = __uint_as_float(acc[q * 8 + 2 * e]) + biasS[bOff + c0 + q * 8 + 2 * e];
-                  float y1 = __uint_as_float(acc[q * 8 + 2 * e + 1]) + biasS[bOff + c0 + q * 8 + 2 * e + 1];
-                  if (L.relu) { y0 = y0 > 0.f ? y0 : 0.f; y1 = y1 > 0.f ? y1 : 0.f; }
-                  const __half2 h = __floats2half2_rn(y0, y1);
-                  packed[e] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                *reinterpret_cast<uint4*>(xRow + (size_t)((c0 >> 3) + q) * kPlaneBytes) =
-                    make_uint4(packed[0], packed[1], packed[2], packed[3]);
-              }
-            }
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(xRow + (size_t)((c >> 3) + q) * kPlaneBytes) = pack8(acc + 8 * q, L.relu != 0);
           }
-          const Layer& Nx = p.layers[l + 1];
-          if (Nx.copyFeatTo >= 0) {
-            for (int f = 0; f < F; f += 8)
-              *reinterpret_cast<uint4*>(xRow + (size_t)((Nx.copyFeatTo + f) >> 3) * kPlaneBytes) =
-                  *reinterpret_cast<const uint4*>(xRow + (size_t)((p.featCol + f) >> 3) * kPlaneBytes);
+          for (; c < c1; c += 8) {
+            uint32_t acc[8];
+            tmem_ld8(laneTaddr + (uint32_t)c, acc);
+            tmem_ld_wait();
+            *reinterpret_cast<uint4*>(xRow + (size_t)(c >> 3) * kPlaneBytes) = pack8(acc, L.relu != 0);
           }
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(actBar);
         }
-        bOff += L.Npad;
       }
     }
   }
