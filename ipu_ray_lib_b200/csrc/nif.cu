@@ -16,6 +16,7 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -303,9 +304,30 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
   if (m->tcOk) {
     const uint32_t tcTiles = (count + tc::kRows - 1) / tc::kRows;
     const uint32_t tcGrid = tcTiles < (uint32_t)sms ? (tcTiles ? tcTiles : 1u) : (uint32_t)sms;  // one persistent CTA per SM
-    tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(m->tc, uvDirect, slotEscape, queue, dCount, count, out);
+    static const bool profile = [] { const char* e = std::getenv("B200RT_NIF_PROFILE"); return e && e[0] == '1'; }();
+    tc::Params params = m->tc;
+    { const char* e = std::getenv("B200RT_NIF_DEBUG_FLAGS"); params.dbgFlags = e ? std::atoi(e) : 0; }
+    unsigned long long* dProf = nullptr;
+    if (profile) {
+      cudaMalloc(&dProf, (size_t)tcGrid * 16 * sizeof(unsigned long long));
+      cudaMemsetAsync(dProf, 0, (size_t)tcGrid * 16 * sizeof(unsigned long long), stream);
+      params.prof = dProf;
+    }
+    tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(params, uvDirect, slotEscape, queue, dCount, count, out);
     const cudaError_t te = cudaGetLastError();
     if (te != cudaSuccess) { g_nifError = cudaGetErrorString(te); return -1; }
+    if (profile) {  // debugging aid: per-role cycle breakdown of CTA 0 (synchronises!)
+      std::vector<unsigned long long> h((size_t)tcGrid * 16);
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h.data(), dProf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      cudaFree(dProf);
+      const char* names[] = {"total", "producer wait empty", "mma wait act", "(unused)", "mma phase (issue..commit)",
+                             "epi wait acc", "epi encode", "epi drain", "tiles"};
+      std::fprintf(stderr, "[nif profile] CTA0 of %u, rows %u:", tcGrid, count);
+      const double tiles = h[tc::PF_TILES] ? (double)h[tc::PF_TILES] : 1.0;
+      for (int i = 0; i < tc::PF_COUNT; ++i) std::fprintf(stderr, " %s=%.0f/tile", names[i], (double)h[i] / tiles);
+      std::fprintf(stderr, "\n");
+    }
     if (launches) *launches += 1;
     return 0;
   }

@@ -13,7 +13,8 @@
 //     TMEM) issued by ONE thread; tcgen05.commit releases ring stages and publishes "accumulator ready";
 //   * the epilogue (8 warps: TMEM lane quarter = warp%4, column half = warp/4) reads the accumulators with
 //     tcgen05.ld, rounds to fp16, applies ReLU on packed halves and writes the next layer's A operand in place.
-// Roles: warps 0-7 = encode + epilogue, warp 8 lane 0 = weight producer, warp 9 lane 0 = MMA issuer.
+// Roles: warps 0-7 = encode + epilogue, warp 8 lane 0 = weight producer, warps 9-10 lane 0 = MMA issuers (one per
+// N-half: a single thread's scalar issue stream costs ~200 cycles per MMA, the pipe needs one every 80).
 #pragma once
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -22,11 +23,12 @@ namespace rt {
 namespace tc {
 
 constexpr int kRows = 128;          // rows (escaped rays) per tile == TMEM lanes
-constexpr int kStages = 4;          // weight ring depth
-constexpr int kStageK = 32;         // K elements per ring stage (2 MMA K-slices)
+constexpr int kStages = 3;          // weight ring depth
+constexpr int kStageK = 64;         // K elements per ring stage (4 MMA K-slices)
 constexpr int kMaxLayers = 16;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kIssuers = 2;          // MMA issuer threads: one per N-half, so two scalar issue streams feed the pipe
+constexpr int kThreads = (kEpiWarps + 1 + kIssuers) * 32;
 constexpr int kPlaneBytes = kRows * 16;  // one K-chunk (8 columns) of the A operand
 constexpr int kStaticPlanesMax = 2 + 8;  // ones slice (2 planes) + up to 64 encoded features
 
@@ -46,7 +48,15 @@ struct Params {
   int stageBytes;       // bytes of one ring stage
   float maxv, mean0, mean1, mean2;
   int logToneMap;
+  int dbgFlags;              // debugging: bit0 = producer signals 'full' without moving weights (timing experiments only)
+  unsigned long long* prof;  // optional [gridDim.x][16] cycle counters (B200RT_NIF_PROFILE=1), else nullptr
 };
+
+// slots of the per-CTA profile record
+enum : int { PF_TOTAL = 0, PF_PROD_WAIT_EMPTY, PF_MMA_WAIT_ACT, PF_MMA_WAIT_FULL, PF_MMA_ISSUE, PF_EPI_WAIT_ACC,
+             PF_EPI_ENCODE, PF_EPI_DRAIN, PF_TILES, PF_COUNT };
+#define NIF_PROF_T0() const long long t0__ = p.prof ? clock64() : 0
+#define NIF_PROF_ADD(var) do { if (p.prof) var += (unsigned long long)(clock64() - t0__); } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -107,8 +117,34 @@ __device__ __forceinline__ void mma_f16(uint32_t dTmem, uint64_t aDesc, uint64_t
       "l"(aDesc), "l"(bDesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same instruction with both descriptors given as (low word, shared high word); executed by a whole converged
+// warp, one elected lane issues (the CUTLASS idiom), so operands stay in uniform registers.
+__device__ __forceinline__ void mma_f16_lo(uint32_t dTmem, uint32_t aLo, uint32_t bLo, uint32_t descHi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}" ::"r"(dTmem),
+      "r"(aLo), "r"(bLo), "r"(descHi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // tcgen05.commit: the mbarrier is arrived on once every previously issued MMA of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {  // whole converged warp calls, one lane commits
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -180,14 +216,17 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
   uint64_t* accBar = bars + 2 * kStages + 1;  // accumulator of the current layer is complete (1 arrival via commit)
   uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform (shuffle from lane 0), so the role branches below are uniform branches and
+  // the issuer's descriptors live in uniform registers instead of being re-broadcast per MMA
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const uint32_t count = uvDirect ? directCount : min(*dCount, directCount);
   const uint32_t numTiles = (count + kRows - 1) / kRows;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(fullBar + s, 1); mbar_init(emptyBar + s, 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(fullBar + s, 1); mbar_init(emptyBar + s, kIssuers); }
     mbar_init(actBar, kEpiWarps * 32);
-    mbar_init(accBar, 1);
+    mbar_init(accBar, kIssuers);
     fence_barrier_init();
   }
   // the ones slice: column 0 = 1.0, columns 1..15 = 0 (the matching weight rows hold the bias and zeros)
@@ -206,6 +245,7 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
     // ===== weight producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      unsigned long long waitEmpty = 0;
       for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
         for (int l = 0; l < p.numLayers; ++l) {
           const Layer& L = p.layers[l];
@@ -214,51 +254,81 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
           for (uint32_t pl = 0; pl < totalPlanes; pl += kStageK / 8) {
             const uint32_t planes = min((uint32_t)(kStageK / 8), totalPlanes - pl);
             const uint32_t bytes = planes * planeBytes;
-            mbar_wait(emptyBar + stage, phase ^ 1u);
-            mbar_expect_tx(fullBar + stage, bytes);
-            bulk_load(ring + (size_t)stage * p.stageBytes,
-                      reinterpret_cast<const unsigned char*>(L.wimg) + (size_t)pl * planeBytes, bytes, fullBar + stage);
+            { NIF_PROF_T0(); mbar_wait(emptyBar + stage, phase ^ 1u); NIF_PROF_ADD(waitEmpty); }
+            if (p.dbgFlags & 1) {
+              mbar_expect_tx(fullBar + stage, 0u);
+            } else {
+              mbar_expect_tx(fullBar + stage, bytes);
+              bulk_load(ring + (size_t)stage * p.stageBytes,
+                        reinterpret_cast<const unsigned char*>(L.wimg) + (size_t)pl * planeBytes, bytes, fullBar + stage);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
+      if (p.prof) p.prof[(size_t)blockIdx.x * 16 + PF_PROD_WAIT_EMPTY] = waitEmpty;
     }
-  } else if (warp == kEpiWarps + 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+  } else if (warp > kEpiWarps) {
+    // ===== MMA issuers: issuer h owns output columns [160 h, 160 h + n_h) =====
+    // The issuing thread is a scalar instruction stream on the critical path of the tensor pipe (one MMA must be
+    // issued every <= 80 cycles per pipe), so the K loop is kept to a handful of 32-bit adds per MMA: only the low
+    // word of a descriptor (start address) changes, everything else is hoisted per layer.
+    const uint32_t issuer = (uint32_t)(warp - kEpiWarps - 1);
+    {
       uint32_t stage = 0, phase = 0, actPhase = 0;
+      unsigned long long waitAct = 0, mmaPhase = 0, tiles = 0;
+      const long long tStart = p.prof ? clock64() : 0;
       const uint32_t xAddr = smem_u32(X), sAddr = smem_u32(S), ringAddr = smem_u32(ring);
+      const uint32_t descHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, version 1 (bit 46)
+      const uint32_t aLoX = ((xAddr >> 4) & 0x3FFFu) | ((uint32_t)(kPlaneBytes >> 4) << 16);
+      const uint32_t aLoS = ((sAddr >> 4) & 0x3FFFu) | ((uint32_t)(kPlaneBytes >> 4) << 16);
+      const uint32_t stageStep = (uint32_t)p.stageBytes >> 4;
+      constexpr uint32_t kSlicesPerStage = kStageK / 16;
       for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
         for (int l = 0; l < p.numLayers; ++l) {
-          const Layer& L = p.layers[l];
-          const uint32_t planeBytesB = (uint32_t)L.Npad * 16u;
-          mbar_wait(actBar, actPhase);
+          const uint32_t actSlices = (uint32_t)p.layers[l].actSlices;
+          const uint32_t slices = actSlices + (uint32_t)p.layers[l].staticSlices;
+          const uint32_t npad = (uint32_t)p.layers[l].Npad;
+          // N per instruction: multiple of 16, at most 256; 320 = 160 + 160 (issuer 0 / issuer 1)
+          const uint32_t n0 = issuer * 160u;
+          const uint32_t nMine = npad > n0 ? (npad - n0 > 160u ? 160u : npad - n0) : 0u;
+          const uint32_t idesc = instr_desc(kRows, (int)(nMine ? nMine : 16u));
+          const uint32_t dTmem = tmemBase + n0;
+          const uint32_t bLoBase = (((ringAddr + n0 * 16u) >> 4) & 0x3FFFu) | (npad << 16);  // LBO = Npad * 16 B
+          const uint32_t bSliceStep = (2u * npad * 16u) >> 4;
+          constexpr uint32_t aSliceStep = (2u * kPlaneBytes) >> 4;
+          { NIF_PROF_T0(); mbar_wait(actBar, actPhase); NIF_PROF_ADD(waitAct); }
           actPhase ^= 1u;
           tc_fence_after();
-          const uint32_t slices = (uint32_t)(L.actSlices + L.staticSlices);
-          for (uint32_t ks = 0; ks < slices; ++ks) {
-            const uint32_t inStage = ks % (kStageK / 16);
-            if (inStage == 0) {
-              mbar_wait(fullBar + stage, phase);
-              tc_fence_after();
+          NIF_PROF_T0();
+          uint32_t aLo = actSlices ? aLoX : aLoS;
+          uint32_t ks = 0;
+          while (ks < slices) {
+            mbar_wait(fullBar + stage, phase);
+            tc_fence_after();
+            uint32_t bLo = bLoBase + stage * stageStep;
+#pragma unroll
+            for (uint32_t j = 0; j < kSlicesPerStage; ++j) {
+              if (ks < slices) {
+                if (ks == actSlices) aLo = aLoS;  // activations exhausted: continue with [ones | encoded input]
+                if (nMine) mma_f16_lo(dTmem, aLo, bLo, descHi, idesc, ks > 0 ? 1u : 0u);
+                aLo += aSliceStep;
+                bLo += bSliceStep;
+                ++ks;
+              }
             }
-            const uint32_t aAddr = ks < (uint32_t)L.actSlices ? xAddr + 2u * ks * kPlaneBytes
-                                                              : sAddr + 2u * (ks - (uint32_t)L.actSlices) * kPlaneBytes;
-            const uint32_t bAddr = ringAddr + stage * (uint32_t)p.stageBytes + inStage * 2u * planeBytesB;
-            const uint64_t aDesc = smem_desc(aAddr, kPlaneBytes, 128u);
-            for (int n0 = 0; n0 < L.Npad; n0 += 160) {
-              int nc = L.Npad - n0;
-              if (nc > 160) nc = 160;  // N per instruction: multiple of 16, at most 256; 320 = 160 + 160
-              const uint64_t bDesc = smem_desc(bAddr + (uint32_t)n0 * 16u, planeBytesB, 128u);
-              mma_f16(tmemBase + (uint32_t)n0, aDesc, bDesc, instr_desc(kRows, nc), ks > 0 ? 1u : 0u);
-            }
-            if (inStage == kStageK / 16 - 1 || ks == slices - 1) {
-              mma_commit(emptyBar + stage);  // stage reusable once these MMAs have read it
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            }
+            mma_commit_elect(emptyBar + stage);  // stage reusable once these MMAs have read it
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          mma_commit(accBar);  // accumulator of layer l complete
+          mma_commit_elect(accBar);  // this issuer's half of the layer-l accumulator is complete
+          NIF_PROF_ADD(mmaPhase);
         }
+        tiles += 1;
+      }
+      if (p.prof && issuer == 0 && lane == 0) {
+        unsigned long long* r = p.prof + (size_t)blockIdx.x * 16;
+        r[PF_TOTAL] = (unsigned long long)(clock64() - tStart);
+        r[PF_MMA_WAIT_ACT] = waitAct; r[PF_MMA_ISSUE] = mmaPhase; r[PF_TILES] = tiles;
       }
     }
   } else {
@@ -269,6 +339,7 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
     unsigned char* sRow = S + (size_t)row * 16;
     const uint32_t laneTaddr = tmemBase + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t accPhase = 0;
+    unsigned long long waitAcc = 0, encodeCyc = 0, drainCyc = 0;
     const int E = p.embed;
     for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
       const uint32_t r = tile * kRows + (uint32_t)row;
@@ -281,6 +352,7 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
       // Encode (src/neural_networks/NifModel.cpp:186-219): half 0 does the u features, half 1 the v features.
       // Feature order: [sin u]_E [sin v]_E [cos u]_E [cos v]_E, parked in S after the ones slice.
       {
+        NIF_PROF_T0();
         const float w = ((half == 0 ? u : v) - 1.f) * 2.f;
         float c = 1.f;
         for (int j = 0; j < E; ++j, c *= 2.f) {
@@ -291,15 +363,17 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
           reinterpret_cast<__half*>(sRow + (size_t)(2 + (fs >> 3)) * kPlaneBytes)[fs & 7] = __float2half_rn(sn);
           reinterpret_cast<__half*>(sRow + (size_t)(2 + (fc >> 3)) * kPlaneBytes)[fc & 7] = __float2half_rn(cs);
         }
+        NIF_PROF_ADD(encodeCyc);
       }
       fence_proxy_async();
       mbar_arrive(actBar);
 
       for (int l = 0; l < p.numLayers; ++l) {
         const Layer& L = p.layers[l];
-        mbar_wait(accBar, accPhase);
+        { NIF_PROF_T0(); mbar_wait(accBar, accPhase); NIF_PROF_ADD(waitAcc); }
         accPhase ^= 1u;
         tc_fence_after();
+        NIF_PROF_T0();
         const bool last = l == p.numLayers - 1;
         if (last) {
           if (half == 0) {
@@ -344,7 +418,12 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
           fence_proxy_async();
           mbar_arrive(actBar);
         }
+        NIF_PROF_ADD(drainCyc);
       }
+    }
+    if (p.prof && threadIdx.x == 0) {
+      unsigned long long* r = p.prof + (size_t)blockIdx.x * 16;
+      r[PF_EPI_WAIT_ACC] = waitAcc; r[PF_EPI_ENCODE] = encodeCyc; r[PF_EPI_DRAIN] = drainCyc;
     }
   }
 
