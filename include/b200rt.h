@@ -84,10 +84,11 @@ typedef struct b200rt_trace_params {
   uint32_t first_sample;       /* path-trace: first sample index (for resuming); default 0 */
   uint32_t num_samples;        /* path-trace: samples to take; 0 = scene.samples_per_pixel */
   uint32_t rays_per_batch;     /* callback granularity; 0 = 8640 * rays_per_worker default (src/IpuScene.cpp:78-108) */
-  uint32_t traversal;          /* 0 = auto (renders: near-first; bare queries: reference order), 1 = reference-order DFS
-                                * (identical visiting order, identical answers for ANY ray), 2 = near-first ordered DFS
-                                * (same answers for unit-length directions, which is all a render produces; ties go to
-                                * the lowest leaf index like the reference's pre-order walk) */
+  uint32_t traversal;          /* 0 = auto (renders: 2; bare queries: 1), 1 = reference-order DFS (identical visiting
+                                * order, identical answers for ANY ray), 2 = near-first ordered DFS (same answers for
+                                * unit-length directions, which is all a render produces; ties go to the lowest leaf
+                                * index like the reference's pre-order walk), 3 = near-first DFS with the path tracer
+                                * run as a warp-scheduled state machine (same arithmetic as 2; measured slower, kept selectable) */
   uint32_t scene_residency;    /* 0 = auto, 1 = BVH staged in shared memory, 2 = global/L2-resident */
   uint32_t samples_per_chunk;  /* path-trace+NIF: samples per wavefront chunk; 0 = auto */
   uint32_t count_visits;       /* 1 = also count node visits / primitive tests (slower; parity tests) */

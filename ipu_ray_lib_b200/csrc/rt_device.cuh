@@ -289,27 +289,37 @@ __device__ __forceinline__ void closest_hit_ordered(const DevScene& sc, const ui
   const Shear sh = make_shear(d);
   hit.t = tMax; hit.geomID = kInvalidGeom; hit.primID = kInvalidPrim; hit.tri = 0; hit.node = 0;
   hit.b0 = hit.b1 = hit.b2 = 0.f;
-  uint32_t stackIdx[kMaxStack];
-  float stackEnter[kMaxStack];
+  // one 8-byte local-memory record per deferred node: {node index, entry distance}
+  uint2 stack[kMaxStack];
   int sp = 0;
 
   NodeWords w = fetch_node<kShared>(nodes, 0);
   if (kCount) cnt.nodeVisits++;
   float enter;
   if (!slab_test(w, o, inv, tMin, hit.t, enter)) return;
+  constexpr uint32_t kDone = 0xFFFFFFFFu;
   uint32_t cur = 0;
   uint32_t meta = w.b.y, geomID = w.c.y >> 16;  // of `cur`
-  while (true) {
-    bool needPop = false;
-    if (geomID != kInvalidGeom) {
-      if (kCount) cnt.primTests++;
-      const LeafResult r = leaf_test(sc, geomID, meta, o, d, tMin, sh);
-      if (r.t > tMin && (r.t < hit.t || (r.t == hit.t && hit.geomID != kInvalidGeom && cur < hit.node))) {
-        hit.t = r.t; hit.geomID = geomID; hit.primID = sc.geoms[geomID].type == 0 ? meta : 0u;
-        hit.tri = r.tri; hit.node = cur; hit.b0 = r.b0; hit.b1 = r.b1; hit.b2 = r.b2;
-      }
-      needPop = true;
-    } else {
+
+  // pop the next deferred node that can still contain a closer hit (the reference's pop-time slab test)
+  auto pop = [&]() {
+    cur = kDone;
+    while (sp > 0) {
+      const uint2 e = stack[--sp];
+      if (!(__uint_as_float(e.y) > hit.t)) { cur = e.x; break; }
+    }
+    if (cur != kDone) {
+      const uint2* p = nodes + 3u * cur;
+      if (kShared) { meta = p[1].y; geomID = p[2].y >> 16; }
+      else { meta = __ldg(p + 1).y; geomID = __ldg(p + 2).y >> 16; }
+    }
+  };
+
+  // "while-while" (Aila & Laine): every lane first descends inner nodes until it HOLDS a leaf (or is done); the
+  // leaf test then runs for all lanes of the warp that hold one, instead of for the one or two lanes that happen
+  // to reach a leaf in a given iteration (ncu: the triangle test ran with 3-6 of 32 lanes active before).
+  while (cur != kDone) {
+    while (cur != kDone && geomID == kInvalidGeom) {
       const uint32_t c0 = cur + 1, c1 = meta;
       const NodeWords w0 = fetch_node<kShared>(nodes, c0);
       const NodeWords w1 = fetch_node<kShared>(nodes, c1);
@@ -319,10 +329,7 @@ __device__ __forceinline__ void closest_hit_ordered(const DevScene& sc, const ui
       const bool h1 = slab_test(w1, o, inv, tMin, hit.t, e1);
       if (h0 && h1) {
         const bool firstNear = !(e1 < e0);  // ties go to the first child, like pre-order
-        const uint32_t farIdx = firstNear ? c1 : c0;
-        stackIdx[sp] = farIdx;
-        stackEnter[sp] = firstNear ? e1 : e0;
-        sp++;
+        stack[sp++] = make_uint2(firstNear ? c1 : c0, __float_as_uint(firstNear ? e1 : e0));
         cur = firstNear ? c0 : c1;
         meta = firstNear ? w0.b.y : w1.b.y;
         geomID = (firstNear ? w0.c.y : w1.c.y) >> 16;
@@ -331,21 +338,17 @@ __device__ __forceinline__ void closest_hit_ordered(const DevScene& sc, const ui
       } else if (h1) {
         cur = c1; meta = w1.b.y; geomID = w1.c.y >> 16;
       } else {
-        needPop = true;
+        pop();
       }
     }
-    if (needPop) {
-      bool found = false;
-      while (sp > 0) {
-        --sp;
-        if (!(stackEnter[sp] > hit.t)) { found = true; break; }
-      }
-      if (!found) break;
-      cur = stackIdx[sp];
-      const uint2* p = nodes + 3u * cur;
-      if (kShared) { meta = p[1].y; geomID = p[2].y >> 16; }
-      else { meta = __ldg(p + 1).y; geomID = __ldg(p + 2).y >> 16; }
+    if (cur == kDone) break;
+    if (kCount) cnt.primTests++;
+    const LeafResult r = leaf_test(sc, geomID, meta, o, d, tMin, sh);
+    if (r.t > tMin && (r.t < hit.t || (r.t == hit.t && hit.geomID != kInvalidGeom && cur < hit.node))) {
+      hit.t = r.t; hit.geomID = geomID; hit.primID = sc.geoms[geomID].type == 0 ? meta : 0u;
+      hit.tri = r.tri; hit.node = cur; hit.b0 = r.b0; hit.b1 = r.b1; hit.b2 = r.b2;
     }
+    pop();
   }
 }
 

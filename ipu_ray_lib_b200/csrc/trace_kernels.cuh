@@ -46,6 +46,7 @@ struct TraceArgs {
   uint32_t* escapeQueue;    // compacted slot indices of escaped samples
   uint32_t* escapeCount;
   float hdriRotation;       // radians
+  int travThreshold;        // state machine: run inner-node steps while at least this many lanes want one
 };
 
 __device__ __forceinline__ void flush_counters(DeviceCounters* out, unsigned closest, unsigned occl, const Counters& c,
@@ -84,7 +85,7 @@ __device__ __forceinline__ void closest_hit(const DevScene& sc, const uint2* nod
 
 // -------------------------------------------------------------------------------------------------
 template <bool kShared, bool kOrdered, bool kCount>
-__global__ void __launch_bounds__(512) shadow_trace_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(768) shadow_trace_kernel(const TraceArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const uint2* nodes = stage_nodes<kShared>(a, reinterpret_cast<uint2*>(smemRaw));
   const DevScene& sc = a.scene;
@@ -149,7 +150,7 @@ __device__ __forceinline__ void escaped_uv(V3 d, float rotation, float& u, float
 }
 
 template <bool kShared, bool kOrdered, bool kCount, bool kNif>
-__global__ void __launch_bounds__(512) path_trace_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(768) path_trace_kernel(const TraceArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const uint2* nodes = stage_nodes<kShared>(a, reinterpret_cast<uint2*>(smemRaw));
   const DevScene& sc = a.scene;
