@@ -175,6 +175,8 @@ def cpu_baseline(args, scene, nif, kind_pref=("port",), seconds=12.0):
     target = max(int(rate * seconds), 20000)
     spp = 4
     stride = max(1, int(w * h * spp / target))
+    if stride == 1:  # fast host: keep every pixel and raise the sample count instead
+        spp = int(max(4, min(args.samples, target // (w * h))))
     dt, cnt, npix = run(stride, spp)
     q = cnt["closest_hit_queries"] + cnt["occlusion_queries"]
     return {
@@ -229,6 +231,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

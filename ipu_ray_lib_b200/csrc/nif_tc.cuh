@@ -341,7 +341,16 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
     uint32_t accPhase = 0;
     unsigned long long waitAcc = 0, encodeCyc = 0, drainCyc = 0;
     const int E = p.embed;
-    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+    // the last layer whose MMAs read the encoded input: once ITS accumulator is complete the feature planes may be
+    // overwritten with the next tile's features, which hides the encode behind the following layer's MMAs
+    int lastFeatLayer = 0;
+    for (int l = 0; l < p.numLayers; ++l)
+      if (p.layers[l].staticSlices > 1) lastFeatLayer = l;
+
+    // Encode (src/neural_networks/NifModel.cpp:186-219): half 0 does the u features, half 1 the v features.
+    // Feature order: [sin u]_E [sin v]_E [cos u]_E [cos v]_E, parked in S after the ones slice. Returns the slot.
+    auto encode_tile = [&](uint32_t tile) -> uint32_t {
+      NIF_PROF_T0();
       const uint32_t r = tile * kRows + (uint32_t)row;
       float u = 0.f, v = 0.f;
       uint32_t slot = 0xFFFFFFFFu;
@@ -349,25 +358,28 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
         if (uvDirect) { slot = r; u = uvDirect[2 * (size_t)r]; v = uvDirect[2 * (size_t)r + 1]; }
         else { slot = queue[r]; u = slotEscape[5 * (size_t)slot + 3]; v = slotEscape[5 * (size_t)slot + 4]; }
       }
-      // Encode (src/neural_networks/NifModel.cpp:186-219): half 0 does the u features, half 1 the v features.
-      // Feature order: [sin u]_E [sin v]_E [cos u]_E [cos v]_E, parked in S after the ones slice.
-      {
-        NIF_PROF_T0();
-        const float w = ((half == 0 ? u : v) - 1.f) * 2.f;
-        float c = 1.f;
-        for (int j = 0; j < E; ++j, c *= 2.f) {
-          const float a = __half2float(__float2half_rn(w * c));
-          float sn, cs;
-          sincosf(a, &sn, &cs);
-          const int fs = half * E + j, fc = 2 * E + half * E + j;
-          reinterpret_cast<__half*>(sRow + (size_t)(2 + (fs >> 3)) * kPlaneBytes)[fs & 7] = __float2half_rn(sn);
-          reinterpret_cast<__half*>(sRow + (size_t)(2 + (fc >> 3)) * kPlaneBytes)[fc & 7] = __float2half_rn(cs);
-        }
-        NIF_PROF_ADD(encodeCyc);
+      const float w = ((half == 0 ? u : v) - 1.f) * 2.f;
+      float c = 1.f;
+      for (int j = 0; j < E; ++j, c *= 2.f) {
+        const float a = __half2float(__float2half_rn(w * c));
+        float sn, cs;
+        sincosf(a, &sn, &cs);
+        const int fs = half * E + j, fc = 2 * E + half * E + j;
+        reinterpret_cast<__half*>(sRow + (size_t)(2 + (fs >> 3)) * kPlaneBytes)[fs & 7] = __float2half_rn(sn);
+        reinterpret_cast<__half*>(sRow + (size_t)(2 + (fc >> 3)) * kPlaneBytes)[fc & 7] = __float2half_rn(cs);
       }
+      NIF_PROF_ADD(encodeCyc);
+      return slot;
+    };
+
+    uint32_t slot = 0xFFFFFFFFu, slotNext = 0xFFFFFFFFu;
+    if (blockIdx.x < numTiles) {
+      slot = encode_tile(blockIdx.x);
       fence_proxy_async();
       mbar_arrive(actBar);
-
+    }
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+      const bool haveNext = tile + gridDim.x < numTiles;
       for (int l = 0; l < p.numLayers; ++l) {
         const Layer& L = p.layers[l];
         { NIF_PROF_T0(); mbar_wait(accBar, accPhase); NIF_PROF_ADD(waitAcc); }
@@ -393,33 +405,53 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
               }
             }
           }
-          tc_fence_before();
         } else {
           // this thread's columns: [c0, c1); the two halves split Npad when it is a multiple of 64
           const bool split = (L.Npad & 63) == 0;
           const int c0 = split ? half * (L.Npad >> 1) : 0;
           const int c1 = split ? c0 + (L.Npad >> 1) : (half == 0 ? L.Npad : 0);
+          const bool relu = L.relu != 0;
+          // software-pipelined drain: the TMEM load of the next 32 columns is in flight while the current 32 are
+          // rounded to fp16 and stored
+          uint32_t bufA[32], bufB[32];
           int c = c0;
-          for (; c + 32 <= c1; c += 32) {
-            uint32_t acc[32];
-            tmem_ld32(laneTaddr + (uint32_t)c, acc);
+          if (c + 32 <= c1) tmem_ld32(laneTaddr + (uint32_t)c, bufA);
+          while (c + 32 <= c1) {
             tmem_ld_wait();
+            const bool moreB = c + 64 <= c1;
+            if (moreB) tmem_ld32(laneTaddr + (uint32_t)(c + 32), bufB);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(xRow + (size_t)((c >> 3) + q) * kPlaneBytes) = pack8(acc + 8 * q, L.relu != 0);
+              *reinterpret_cast<uint4*>(xRow + (size_t)((c >> 3) + q) * kPlaneBytes) = pack8(bufA + 8 * q, relu);
+            c += 32;
+            if (moreB) {
+              tmem_ld_wait();
+              if (c + 64 <= c1) tmem_ld32(laneTaddr + (uint32_t)(c + 32), bufA);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(xRow + (size_t)((c >> 3) + q) * kPlaneBytes) = pack8(bufB + 8 * q, relu);
+              c += 32;
+            }
           }
           for (; c < c1; c += 8) {
             uint32_t acc[8];
             tmem_ld8(laneTaddr + (uint32_t)c, acc);
             tmem_ld_wait();
-            *reinterpret_cast<uint4*>(xRow + (size_t)(c >> 3) * kPlaneBytes) = pack8(acc, L.relu != 0);
+            *reinterpret_cast<uint4*>(xRow + (size_t)(c >> 3) * kPlaneBytes) = pack8(acc, relu);
           }
+        }
+        NIF_PROF_ADD(drainCyc);
+        // release the next layer (or the next tile's first layer); before the LAST release of a tile the next
+        // tile's features must already be in place
+        if (last && haveNext && lastFeatLayer >= l) slotNext = encode_tile(tile + gridDim.x);
+        if (!last || haveNext) {
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(actBar);
         }
-        NIF_PROF_ADD(drainCyc);
+        if (!last && haveNext && l == lastFeatLayer) slotNext = encode_tile(tile + gridDim.x);
       }
+      slot = slotNext;
     }
     if (p.prof && threadIdx.x == 0) {
       unsigned long long* r = p.prof + (size_t)blockIdx.x * 16;
