@@ -19,7 +19,7 @@ HOST  := $(PKG)/host
 
 all: $(PKG)/libb200rt.so $(PKG)/libb200rt_scene.so $(PKG)/trace oracle
 
-$(CSRC)/b200rt.o: $(CSRC)/b200rt.cu $(CSRC)/trace_kernels.cuh $(CSRC)/path_trace_sm.cuh $(CSRC)/rt_device.cuh $(CSRC)/rt_math.h \
+$(CSRC)/b200rt.o: $(CSRC)/b200rt.cu $(CSRC)/trace_kernels.cuh $(CSRC)/path_trace_sm.cuh $(CSRC)/wavefront.cuh $(CSRC)/rt_device.cuh $(CSRC)/rt_math.h \
                   $(CSRC)/sin_deg_table.inc $(CSRC)/nif.cuh include/b200rt.h
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 

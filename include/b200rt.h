@@ -88,7 +88,9 @@ typedef struct b200rt_trace_params {
                                 * order, identical answers for ANY ray), 2 = near-first ordered DFS (same answers for
                                 * unit-length directions, which is all a render produces; ties go to the lowest leaf
                                 * index like the reference's pre-order walk), 3 = near-first DFS with the path tracer
-                                * run as a warp-scheduled state machine (same arithmetic as 2; measured slower, kept selectable) */
+                                * run as a warp-scheduled state machine (same arithmetic as 2; measured slower, kept selectable),
+                                * 4 = wavefront path tracer: per-bounce generate / trace / shade kernels over path queues in
+                                * HBM (same arithmetic and results as 2; measured on par, kept selectable) */
   uint32_t scene_residency;    /* 0 = auto, 1 = BVH staged in shared memory, 2 = global/L2-resident */
   uint32_t samples_per_chunk;  /* path-trace+NIF: samples per wavefront chunk; 0 = auto */
   uint32_t count_visits;       /* 1 = also count node visits / primitive tests (slower; parity tests) */

@@ -19,6 +19,7 @@
 #include "nif.cuh"
 #include "path_trace_sm.cuh"
 #include "trace_kernels.cuh"
+#include "wavefront.cuh"
 
 namespace {
 
@@ -85,6 +86,7 @@ struct b200rt_scene {
   DeviceBuffer workCounter, counters;
   DeviceBuffer rays;                                   // device copy of the stream (host-buffer entry point)
   DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
+  DeviceBuffer wfRayO, wfRayD, wfNrm, wfThr, wfCol, wfRng, wfHitA, wfHitB, wfQ0, wfQ1, wfCounts;  // wavefront path state
   b200rt_trace_stats stats{};
   float hdriRotationDegrees = 0.f;
   size_t maxNifBatch = 0;
@@ -95,7 +97,8 @@ struct b200rt_scene {
     if (nif) rt::nif_destroy(nif);
     for (DeviceBuffer* b : {&nodes, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
                             &workCounter, &counters, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
-                            &escapeCount})
+                            &escapeCount, &wfRayO, &wfRayD, &wfNrm, &wfThr, &wfCol, &wfRng, &wfHitA, &wfHitB, &wfQ0, &wfQ1,
+                            &wfCounts})
       b->release();
     if (evStart) cudaEventDestroy(evStart);
     if (evStop) cudaEventDestroy(evStop);
@@ -296,7 +299,8 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
     a.rngKey = rt::splitmix64(sc.desc.rng_seed);
     const uint32_t first = p.first_sample;
     const uint32_t count = p.num_samples ? p.num_samples : sc.desc.samples_per_pixel;
-    if (!sc.nif) {
+    const bool wavefront = p.traversal == 4;
+    if (!sc.nif && !wavefront) {
       a.firstSample = first;
       a.endSample = first + count;
       CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
@@ -305,44 +309,101 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
       timer.end(sc.stream);
       launches += 1;
     } else {
-      // Wavefront over chunks of samples: trace -> (compacted escaped rays) NIF -> ordered accumulate.
+      // Chunks of samples: trace -> (compacted escaped rays) NIF -> ordered accumulate.
       uint32_t chunk = p.samples_per_chunk ? p.samples_per_chunk : 32u;
-      // bound the slot arrays to ~8 GiB
-      const size_t perSlot = (3 + 5 + 3 + 1) * sizeof(float);
-      while (chunk > 1 && (size_t)chunk * n * perSlot > (size_t)8 << 30) chunk /= 2;
+      // bound the per-path arrays (slots; plus 136 B of path state in wavefront mode) to ~8 / ~20 GiB
+      const size_t perSlot = (3 + 5 + 3 + 1) * sizeof(float) + (wavefront ? 136 : 0);
+      const size_t budget = wavefront ? (size_t)20 << 30 : (size_t)8 << 30;
+      while (chunk > 1 && (size_t)chunk * n * perSlot > budget) chunk /= 2;
       if (chunk > count) chunk = count ? count : 1;
-      CU_TRY(sc.slotColor.reserve((size_t)chunk * n * 3 * sizeof(float)));
-      CU_TRY(sc.slotEscape.reserve((size_t)chunk * n * 5 * sizeof(float)));
-      CU_TRY(sc.slotEnv.reserve((size_t)chunk * n * 3 * sizeof(float)));
-      CU_TRY(sc.escapeQueue.reserve((size_t)chunk * n * sizeof(uint32_t)));
+      if ((size_t)chunk * n > 0xFFFFFFF0ull) return fail(B200RT_ERR_UNSUPPORTED, "ray stream too long for one chunk");
+      const size_t P = (size_t)chunk * n;
+      CU_TRY(sc.slotColor.reserve(P * 3 * sizeof(float)));
+      CU_TRY(sc.slotEscape.reserve(P * 5 * sizeof(float)));
+      CU_TRY(sc.slotEnv.reserve(P * 3 * sizeof(float)));
+      CU_TRY(sc.escapeQueue.reserve(P * sizeof(uint32_t)));
       CU_TRY(sc.escapeCount.reserve(16));
       a.slotColor = (float*)sc.slotColor.p;
       a.slotEscape = (float*)sc.slotEscape.p;
       a.escapeQueue = (uint32_t*)sc.escapeQueue.p;
       a.escapeCount = (uint32_t*)sc.escapeCount.p;
       a.hdriRotation = (sc.hdriRotationDegrees / 360.f) * (float)(2.0 * M_PI);  // src/IpuScene.cpp:641
+      rt::WfArgs w{};
+      if (wavefront) {
+        for (DeviceBuffer* b : {&sc.wfRayO, &sc.wfRayD, &sc.wfNrm, &sc.wfThr, &sc.wfCol, &sc.wfRng, &sc.wfHitA, &sc.wfHitB})
+          CU_TRY(b->reserve(P * 16));
+        CU_TRY(sc.wfQ0.reserve(P * 4));
+        CU_TRY(sc.wfQ1.reserve(P * 4));
+        CU_TRY(sc.wfCounts.reserve(16));
+        w.b.rayO = (float4*)sc.wfRayO.p; w.b.rayD = (float4*)sc.wfRayD.p; w.b.nrm = (float4*)sc.wfNrm.p;
+        w.b.thr = (float4*)sc.wfThr.p; w.b.col = (float4*)sc.wfCol.p; w.b.rng = (uint4*)sc.wfRng.p;
+        w.b.hitA = (float4*)sc.wfHitA.p; w.b.hitB = (float4*)sc.wfHitB.p;
+        w.b.queue[0] = (uint32_t*)sc.wfQ0.p; w.b.queue[1] = (uint32_t*)sc.wfQ1.p;
+        w.b.counts = (uint32_t*)sc.wfCounts.p;
+        w.lastSample = first + count - 1;
+        static const int envWf = [] { const char* e = std::getenv("B200RT_WF_THRESHOLD"); return e ? std::atoi(e) : 20; }();
+        w.travThreshold = envWf;
+      }
       for (uint32_t s0 = first; s0 < first + count; s0 += chunk) {
         const uint32_t c = std::min(chunk, first + count - s0);
         a.firstSample = s0;
         a.endSample = s0 + c;
-        CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
         CU_TRY(cudaMemsetAsync(sc.escapeCount.p, 0, 4, sc.stream));
-        timer.begin(KernelTimer::TRACE, sc.stream);
-        CU_TRY(run_path(sc, L, true, a));
-        timer.end(sc.stream);
-        launches += 1;
-        int nifLaunches = 0;
-        timer.begin(KernelTimer::NIF, sc.stream);
-        const int rc = rt::nif_eval_queue(sc.nif, (const float*)sc.slotEscape.p, (const uint32_t*)sc.escapeQueue.p,
-                                          (const uint32_t*)sc.escapeCount.p, (uint32_t)std::min<size_t>((size_t)c * n, 0xFFFFFFFFull),
-                                          (float*)sc.slotEnv.p, sc.stream, &nifLaunches);
-        timer.end(sc.stream);
-        if (rc != 0) return fail(B200RT_ERR_CUDA, std::string("NIF evaluation failed: ") + rt::nif_last_error());
-        launches += (uint64_t)nifLaunches;
+        if (!wavefront) {
+          CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
+          timer.begin(KernelTimer::TRACE, sc.stream);
+          CU_TRY(run_path(sc, L, true, a));
+          timer.end(sc.stream);
+          launches += 1;
+        } else {
+          w.t = a;
+          w.chunk = c;
+          w.numPaths = (uint32_t)((size_t)c * n);
+          const int gridSmall = sc.numSMs * 8;
+          timer.begin(KernelTimer::TRACE, sc.stream);
+          CU_TRY(cudaMemsetAsync(sc.wfCounts.p, 0, 16, sc.stream));
+          rt::wf_generate_kernel<<<gridSmall, 256, 0, sc.stream>>>(w);
+          CU_TRY(cudaGetLastError());
+          launches += 1;
+          for (uint32_t b = 0; b < sc.desc.max_path_length; ++b) {
+            w.qIn = (int)(b & 1u);
+            CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + 2, 0, 4, sc.stream));            // fetch cursor
+            CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + (w.qIn ^ 1), 0, 4, sc.stream));  // next queue size
+            {
+              cudaError_t e;
+              if (L.shared) {
+                auto k = L.count ? rt::wf_trace_kernel<true, true> : rt::wf_trace_kernel<true, false>;
+                e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+                if (e == cudaSuccess) { k<<<L.grid, L.block, L.smem, sc.stream>>>(w); e = cudaGetLastError(); }
+              } else {
+                auto k = L.count ? rt::wf_trace_kernel<false, true> : rt::wf_trace_kernel<false, false>;
+                k<<<L.grid, L.block, 0, sc.stream>>>(w);
+                e = cudaGetLastError();
+              }
+              CU_TRY(e);
+            }
+            if (sc.nif) rt::wf_shade_kernel<true><<<gridSmall, 256, 0, sc.stream>>>(w);
+            else rt::wf_shade_kernel<false><<<gridSmall, 256, 0, sc.stream>>>(w);
+            CU_TRY(cudaGetLastError());
+            launches += 2;
+          }
+          timer.end(sc.stream);
+        }
+        if (sc.nif) {
+          int nifLaunches = 0;
+          timer.begin(KernelTimer::NIF, sc.stream);
+          const int rc = rt::nif_eval_queue(sc.nif, (const float*)sc.slotEscape.p, (const uint32_t*)sc.escapeQueue.p,
+                                            (const uint32_t*)sc.escapeCount.p, (uint32_t)std::min<size_t>((size_t)c * n, 0xFFFFFFFFull),
+                                            (float*)sc.slotEnv.p, sc.stream, &nifLaunches);
+          timer.end(sc.stream);
+          if (rc != 0) return fail(B200RT_ERR_CUDA, std::string("NIF evaluation failed: ") + rt::nif_last_error());
+          launches += (uint64_t)nifLaunches;
+        }
         const uint32_t threads = 256, blocks = (uint32_t)((n + threads - 1) / threads);
         timer.begin(KernelTimer::ACCUM, sc.stream);
-        rt::accumulate_kernel<<<blocks, threads, 0, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,
-                                                                 (const float*)sc.slotEscape.p, (const float*)sc.slotEnv.p);
+        rt::wf_accumulate_kernel<<<blocks, threads, 0, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,
+                                                                    (const float*)sc.slotEscape.p,
+                                                                    sc.nif ? (const float*)sc.slotEnv.p : nullptr);
         timer.end(sc.stream);
         CU_TRY(cudaGetLastError());
         launches += 1;

@@ -306,7 +306,6 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
     const uint32_t tcGrid = tcTiles < (uint32_t)sms ? (tcTiles ? tcTiles : 1u) : (uint32_t)sms;  // one persistent CTA per SM
     static const bool profile = [] { const char* e = std::getenv("B200RT_NIF_PROFILE"); return e && e[0] == '1'; }();
     tc::Params params = m->tc;
-    { const char* e = std::getenv("B200RT_NIF_DEBUG_FLAGS"); params.dbgFlags = e ? std::atoi(e) : 0; }
     unsigned long long* dProf = nullptr;
     if (profile) {
       cudaMalloc(&dProf, (size_t)tcGrid * 16 * sizeof(unsigned long long));

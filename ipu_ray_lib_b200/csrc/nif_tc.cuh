@@ -48,7 +48,6 @@ struct Params {
   int stageBytes;       // bytes of one ring stage
   float maxv, mean0, mean1, mean2;
   int logToneMap;
-  int dbgFlags;              // debugging: bit0 = producer signals 'full' without moving weights (timing experiments only)
   unsigned long long* prof;  // optional [gridDim.x][16] cycle counters (B200RT_NIF_PROFILE=1), else nullptr
 };
 
@@ -255,13 +254,9 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
             const uint32_t planes = min((uint32_t)(kStageK / 8), totalPlanes - pl);
             const uint32_t bytes = planes * planeBytes;
             { NIF_PROF_T0(); mbar_wait(emptyBar + stage, phase ^ 1u); NIF_PROF_ADD(waitEmpty); }
-            if (p.dbgFlags & 1) {
-              mbar_expect_tx(fullBar + stage, 0u);
-            } else {
-              mbar_expect_tx(fullBar + stage, bytes);
-              bulk_load(ring + (size_t)stage * p.stageBytes,
-                        reinterpret_cast<const unsigned char*>(L.wimg) + (size_t)pl * planeBytes, bytes, fullBar + stage);
-            }
+            mbar_expect_tx(fullBar + stage, bytes);
+            bulk_load(ring + (size_t)stage * p.stageBytes,
+                      reinterpret_cast<const unsigned char*>(L.wimg) + (size_t)pl * planeBytes, bytes, fullBar + stage);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }

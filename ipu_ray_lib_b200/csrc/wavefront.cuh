@@ -1,0 +1,375 @@
+// Wavefront path tracer: rays stream through HBM as float4 SoA records and are regrouped between bounces.
+//
+// The megakernel (path_trace_kernel) runs one BVH query per lane in lockstep, so a warp works at the pace of its
+// slowest traversal: with ~10 inner-node steps on average and a long tail, ncu measured ~8 of 32 lanes active in the
+// traversal loop. Here the per-path state lives in HBM between bounces and three kernels split the work:
+//
+//   wf_generate  one thread per (pixel, sample) of the chunk: per-(pixel,sample) RNG stream, jittered camera ray,
+//                first offsetRay; all paths enter queue 0
+//   wf_trace     persistent warps; every lane pulls ray ids from the bounce's queue ON ITS OWN and pulls the next one
+//                the moment its traversal ends, so lanes never wait for a neighbour's long traversal; inside, each
+//                warp iteration runs one phase chosen by ballot (inner-node steps while enough lanes want one, else
+//                leaf tests, else the fetch of new rays)
+//   wf_shade     one thread per surviving path: updateHit, material, BxDF sample, roulette; writes the next ray (offset
+//                already applied) and compacts survivors into the other queue with a warp-aggregated append; finished
+//                paths write their colour / escape record (and the HitRecord if they are the last sample)
+//
+// The arithmetic per path is the megakernel's, statement for statement, so results are bit-identical; only the
+// grouping of work changes. rgb is accumulated afterwards in sample order by accumulate_kernel.
+#pragma once
+#include "trace_kernels.cuh"
+
+namespace rt {
+
+struct WfBuffers {
+  float4* rayO;       // [P] origin.xyz (offset applied), w = tMax of the last intersect (HitRecord::r.tMax)
+  float4* rayD;       // [P] direction.xyz
+  float4* nrm;        // [P] normal.xyz, w = primID bits
+  float4* thr;        // [P] throughput.xyz, w = (geomID | flags << 16) bits
+  float4* col;        // [P] colour.xyz, w = bounce bits
+  uint4* rng;         // [P] xoroshiro state {s0.lo, s0.hi, s1.lo, s1.hi}
+  float4* hitA;       // [P] t, geomID bits, primID bits, tri bits
+  float4* hitB;       // [P] b0, b1, b2
+  uint32_t* queue[2];  // [P] path ids of the current / next bounce
+  uint32_t* counts;   // [0],[1] queue sizes, [2] fetch cursor of wf_trace
+};
+
+struct WfArgs {
+  TraceArgs t;        // scene, rays, sample range, camera, NIF slot arrays ...
+  WfBuffers b;
+  uint32_t numPaths;  // numRays * chunk
+  uint32_t chunk;
+  uint32_t lastSample;  // the sample whose HitRecord is left in the ray stream (last of the whole call)
+  int qIn;            // queue index read by this launch
+  int travThreshold;
+  int writeRgbDirect; // unused (rgb is always accumulated by accumulate_kernel)
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wf_generate_kernel(const WfArgs a) {
+  const TraceArgs& t = a.t;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < a.numPaths; p += gridDim.x * blockDim.x) {
+    const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
+    const uint32_t s = t.firstSample + c;
+    const float* tr = t.rays + (size_t)idx * TR_WORDS;
+    const float row = tr[TR_ROW], col = tr[TR_COL];
+    const uint32_t pixelIndex = (uint32_t)row * (uint32_t)t.imageWidth + (uint32_t)col;
+    // sampleCameraRays (codelets/TraceCodelets.cpp:142-164) with the per-(pixel,sample) stream
+    Rng rng;
+    rng_seed_stream(rng, t.rngKey, pixelIndex, s);
+    const uint64_t ra = rng_next(rng), rb = rng_next(rng);
+    float g0, g1;
+    gaussian_pair(ra, rb, g0, g1);
+    const float pu = row + t.antiAlias * g0;
+    const float pv = col + t.antiAlias * g1;
+    const V3 d = pixel_to_ray_dir(pv, pu, t.imageWidth, t.imageHeight, t.tanTheta);
+    const V3 n = mk(0.f, 0.f, 1.f);
+    const V3 o = offset_origin(mk(0.f, 0.f, 0.f), d, n);  // first offsetRay of the bounce loop (trace.cpp:126)
+    a.b.rayO[p] = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
+    a.b.rayD[p] = make_float4(d.x, d.y, d.z, 0.f);
+    a.b.nrm[p] = make_float4(n.x, n.y, n.z, __uint_as_float(kInvalidPrim));
+    a.b.thr[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(kInvalidGeom));
+    a.b.col[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+    a.b.rng[p] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
+    a.b.queue[0][p] = p;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[0] = a.numPaths;
+}
+
+// ------------------------------------------------------------------------------------------------
+enum : int { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2, WF_DONE = 3 };
+
+template <bool kShared, bool kCount>
+__global__ void __launch_bounds__(768) wf_trace_kernel(const WfArgs a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const uint2* nodes = stage_nodes<kShared>(a.t, reinterpret_cast<uint2*>(smemRaw));
+  const DevScene& sc = a.t.scene;
+  const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
+  const float inf = __int_as_float(0x7f800000);
+  const uint32_t* queue = a.b.queue[a.qIn];
+  const uint32_t count = a.b.counts[a.qIn];
+  uint32_t* cursor = a.b.counts + 2;
+  Counters cnt = {0u, 0u};
+  unsigned nClosest = 0;
+
+  V3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 0.f, -1.f), inv = mk(0.f, 0.f, 0.f);
+  Shear sh;
+  sh.kz = 2; sh.sx = sh.sy = sh.sz = 0.f;
+  Hit hit;
+  hit.t = inf; hit.geomID = kInvalidGeom; hit.primID = kInvalidPrim; hit.tri = 0; hit.node = 0;
+  hit.b0 = hit.b1 = hit.b2 = 0.f;
+  uint32_t cur = 0, meta = 0, curGeom = kInvalidGeom, path = 0xFFFFFFFFu;
+  uint2 stack[kMaxStack];
+  int sp = 0;
+  int phase = WF_FETCH;
+
+  auto pop_next = [&]() {
+    bool found = false;
+    uint2 e = make_uint2(0u, 0u);
+    while (sp > 0) {
+      e = stack[--sp];
+      if (!(__uint_as_float(e.y) > hit.t)) { found = true; break; }
+    }
+    if (!found) { phase = WF_FETCH; return; }
+    cur = e.x;
+    const uint2* p = nodes + 3u * cur;
+    if (kShared) { meta = p[1].y; curGeom = p[2].y >> 16; }
+    else { meta = __ldg(p + 1).y; curGeom = __ldg(p + 2).y >> 16; }
+    phase = curGeom != kInvalidGeom ? WF_LEAF : WF_TRAV;
+  };
+
+  while (true) {
+    const unsigned mT = __ballot_sync(full, phase == WF_TRAV);
+    const unsigned mL = __ballot_sync(full, phase == WF_LEAF);
+    const unsigned mF = __ballot_sync(full, phase == WF_FETCH);
+    if (!(mT | mL | mF)) break;
+    const int cT = __popc(mT), cL = __popc(mL), cF = __popc(mF);
+    int pick;
+    if (cT >= a.travThreshold || (cT >= cL && cT >= cF)) pick = WF_TRAV;
+    else if (cL >= cF) pick = WF_LEAF;
+    else pick = WF_FETCH;
+
+    if (pick == WF_TRAV) {
+      if (phase == WF_TRAV) {
+        const uint32_t c0 = cur + 1, c1 = meta;
+        const NodeWords w0 = fetch_node<kShared>(nodes, c0);
+        const NodeWords w1 = fetch_node<kShared>(nodes, c1);
+        if (kCount) cnt.nodeVisits += 2;
+        float e0, e1;
+        const bool h0 = slab_test(w0, o, inv, 0.f, hit.t, e0);
+        const bool h1 = slab_test(w1, o, inv, 0.f, hit.t, e1);
+        if (h0 && h1) {
+          const bool firstNear = !(e1 < e0);  // ties go to the first child, like pre-order
+          stack[sp++] = make_uint2(firstNear ? c1 : c0, __float_as_uint(firstNear ? e1 : e0));
+          cur = firstNear ? c0 : c1;
+          meta = firstNear ? w0.b.y : w1.b.y;
+          curGeom = (firstNear ? w0.c.y : w1.c.y) >> 16;
+          if (curGeom != kInvalidGeom) phase = WF_LEAF;
+        } else if (h0) {
+          cur = c0; meta = w0.b.y; curGeom = w0.c.y >> 16;
+          if (curGeom != kInvalidGeom) phase = WF_LEAF;
+        } else if (h1) {
+          cur = c1; meta = w1.b.y; curGeom = w1.c.y >> 16;
+          if (curGeom != kInvalidGeom) phase = WF_LEAF;
+        } else {
+          pop_next();
+        }
+      }
+    } else if (pick == WF_LEAF) {
+      if (phase == WF_LEAF) {
+        if (kCount) cnt.primTests++;
+        const LeafResult r = leaf_test(sc, curGeom, meta, o, d, 0.f, sh);
+        if (r.t > 0.f && (r.t < hit.t || (r.t == hit.t && hit.geomID != kInvalidGeom && cur < hit.node))) {
+          hit.t = r.t; hit.geomID = curGeom; hit.primID = sc.geoms[curGeom].type == 0 ? meta : 0u;
+          hit.tri = r.tri; hit.node = cur; hit.b0 = r.b0; hit.b1 = r.b1; hit.b2 = r.b2;
+        }
+        pop_next();
+      }
+    } else {
+      // lanes that finished a query store its result and claim the next ray id together
+      uint32_t claimBase = 0;
+      {
+        const int leader = __ffs(mF) - 1;
+        if ((int)lane == leader) claimBase = atomicAdd(cursor, (uint32_t)cF);
+        claimBase = __shfl_sync(full, claimBase, leader);
+      }
+      if (phase == WF_FETCH) {
+        if (path != 0xFFFFFFFFu) {
+          a.b.hitA[path] = make_float4(hit.t, __uint_as_float(hit.geomID), __uint_as_float(hit.primID), __uint_as_float(hit.tri));
+          a.b.hitB[path] = make_float4(hit.b0, hit.b1, hit.b2, 0.f);
+        }
+        const uint32_t qi = claimBase + (uint32_t)__popc(mF & ((1u << lane) - 1u));
+        if (qi >= count) {
+          path = 0xFFFFFFFFu;
+          phase = WF_DONE;
+        } else {
+          path = queue[qi];
+          const float4 ro = a.b.rayO[path], rd = a.b.rayD[path];
+          o = mk(ro.x, ro.y, ro.z);
+          d = mk(rd.x, rd.y, rd.z);
+          // start of CompactBvh::intersect (tMin = 0, tMax = inf as set by the bounce loop, trace.cpp:128-130)
+          nClosest++;
+          inv = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
+          sh = make_shear(d);
+          hit.t = inf; hit.geomID = kInvalidGeom; hit.primID = kInvalidPrim; hit.tri = 0; hit.node = 0;
+          hit.b0 = hit.b1 = hit.b2 = 0.f;
+          sp = 0;
+          const NodeWords w = fetch_node<kShared>(nodes, 0);
+          if (kCount) cnt.nodeVisits++;
+          float enter;
+          if (!slab_test(w, o, inv, 0.f, hit.t, enter)) {
+            phase = WF_FETCH;  // missed the scene: result (no hit) is stored on the next fetch step
+          } else {
+            cur = 0; meta = w.b.y; curGeom = w.c.y >> 16;
+            phase = curGeom != kInvalidGeom ? WF_LEAF : WF_TRAV;
+          }
+        }
+      }
+    }
+  }
+  flush_counters(a.t.counters, nClosest, 0u, cnt, 0u, 0u);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool kNif>
+__global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
+  const TraceArgs& t = a.t;
+  const DevScene& sc = t.scene;
+  const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
+  const uint32_t* queueIn = a.b.queue[a.qIn];
+  uint32_t* queueOut = a.b.queue[a.qIn ^ 1];
+  const uint32_t count = a.b.counts[a.qIn];
+  uint32_t* countOut = a.b.counts + (a.qIn ^ 1);
+  unsigned nSamples = 0, nEscaped = 0;
+  // whole warps iterate together so the ballots below see converged lanes
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (count + stride - 1) / stride;
+  for (uint32_t r = 0; r < rounds; ++r) {
+    const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < count;
+    bool survive = false;
+    uint32_t appendSlot = 0xFFFFFFFFu, p = 0;
+    if (valid) {
+      p = queueIn[i];
+      const float4 ha = a.b.hitA[p], hb = a.b.hitB[p];
+      const float4 ro = a.b.rayO[p], rd = a.b.rayD[p], nn = a.b.nrm[p], th = a.b.thr[p], cl = a.b.col[p];
+      const uint4 rs = a.b.rng[p];
+      Hit hit;
+      hit.t = ha.x; hit.geomID = __float_as_uint(ha.y); hit.primID = __float_as_uint(ha.z); hit.tri = __float_as_uint(ha.w);
+      hit.node = 0; hit.b0 = hb.x; hit.b1 = hb.y; hit.b2 = hb.z;
+      V3 o = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z), n = mk(nn.x, nn.y, nn.z);
+      V3 thr = mk(th.x, th.y, th.z), color = mk(cl.x, cl.y, cl.z);
+      uint32_t primID = __float_as_uint(nn.w);
+      uint32_t geomID = __float_as_uint(th.w) & 0xffffu, flags = __float_as_uint(th.w) >> 16;
+      uint32_t bounce = __float_as_uint(cl.w);
+      Rng rng;
+      rng.s0 = (uint64_t)rs.x | ((uint64_t)rs.y << 32);
+      rng.s1 = (uint64_t)rs.z | ((uint64_t)rs.w << 32);
+      if (bounce == 0) nSamples++;
+
+      // ---- rest of one bounce-loop iteration (trace.cpp:133-184) ----
+      bool ended = false, escaped = false;
+      const float tMaxOut = hit.t;
+      if (hit.geomID != kInvalidGeom) {
+        geomID = hit.geomID; primID = hit.primID;
+        o = o + d * hit.t;
+        n = hit_normal(sc, hit, o);
+        const Mat m = load_material(sc, geomID);
+        if (m.emissive) color = color + thr * m.emission;
+        if (m.type == 0) {
+          const float u1 = rng_uniform(rng);
+          const float u2 = rng_uniform(rng);
+          d = sample_diffuse(n, u1, u2);
+          thr = thr * m.albedo;
+        } else if (m.type == 1) {
+          d = reflect_dir(d, n);
+          thr = thr * m.albedo;
+        } else if (m.type == 2) {
+          const float u1 = rng_uniform(rng);
+          bool refracted;
+          d = dielectric_dir(d, n, m.ior, u1, refracted);
+          if (refracted) thr = thr * m.albedo;
+        } else {
+          color = color * __int_as_float(0x7fc00000);  // poisons rgb like result.rgb *= NaN (trace.cpp:167)
+          flags |= kFlagError;
+        }
+      } else {
+        flags |= kFlagEscaped;
+        ended = true;
+        escaped = true;
+      }
+      if (!ended) {
+        if (bounce > t.rouletteStartDepth) {
+          const float u1 = rng_uniform(rng);
+          const float pr = maxc(thr);  // evaluateRoulette (geometric_sampling.hpp:56-63)
+          if (pr == 0.f || u1 > pr) ended = true;
+          else thr = thr * (1.f / pr);
+        }
+        bounce++;
+        if (bounce >= t.maxPathLength) ended = true;
+      }
+
+      const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
+      const uint32_t s = t.firstSample + c;
+      if (!ended) {
+        const V3 on = offset_origin(o, d, n);  // offsetRay at the top of the next iteration (trace.cpp:126)
+        a.b.rayO[p] = make_float4(on.x, on.y, on.z, tMaxOut);
+        a.b.rayD[p] = make_float4(d.x, d.y, d.z, 0.f);
+        a.b.nrm[p] = make_float4(n.x, n.y, n.z, __uint_as_float(primID));
+        a.b.thr[p] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(geomID | (flags << 16)));
+        a.b.col[p] = make_float4(color.x, color.y, color.z, __uint_as_float(bounce));
+        a.b.rng[p] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
+        survive = true;
+      } else {
+        if (escaped) nEscaped++;
+        float* sc3 = t.slotColor + 3 * (size_t)p;
+        sc3[0] = color.x; sc3[1] = color.y; sc3[2] = color.z;
+        if (kNif) {
+          float* se = t.slotEscape + 5 * (size_t)p;
+          float u = -1.f, v = 0.f;
+          if (escaped) escaped_uv(d, t.hdriRotation, u, v);
+          se[0] = thr.x; se[1] = thr.y; se[2] = thr.z; se[3] = u; se[4] = v;
+          if (escaped) appendSlot = p;
+        }
+        if (s == a.lastSample) {
+          // the HitRecord the reference leaves in the stream is the last sample's
+          float* tr = t.rays + (size_t)idx * TR_WORDS;
+          tr[TR_ORIGIN] = o.x; tr[TR_ORIGIN + 1] = o.y; tr[TR_ORIGIN + 2] = o.z;
+          tr[TR_TMIN] = 0.f;
+          tr[TR_DIR] = d.x; tr[TR_DIR + 1] = d.y; tr[TR_DIR + 2] = d.z;
+          tr[TR_TMAX] = tMaxOut;
+          tr[TR_PRIM] = __uint_as_float(primID);
+          tr[TR_NORMAL] = n.x; tr[TR_NORMAL + 1] = n.y; tr[TR_NORMAL + 2] = n.z;
+          tr[TR_THROUGHPUT] = thr.x; tr[TR_THROUGHPUT + 1] = thr.y; tr[TR_THROUGHPUT + 2] = thr.z;
+          tr[TR_IDS] = __uint_as_float(geomID | (flags << 16));
+        }
+      }
+    }
+    // regroup: survivors go to the other queue, escaped slots to the NIF queue (warp-aggregated appends)
+    {
+      const unsigned m = __ballot_sync(full, survive);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(countOut, (uint32_t)__popc(m));
+        base = __shfl_sync(full, base, leader);
+        if (survive) queueOut[base + __popc(m & ((1u << lane) - 1u))] = p;
+      }
+    }
+    if (kNif) {
+      const unsigned m = __ballot_sync(full, appendSlot != 0xFFFFFFFFu);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(t.escapeCount, (uint32_t)__popc(m));
+        base = __shfl_sync(full, base, leader);
+        if (appendSlot != 0xFFFFFFFFu) t.escapeQueue[base + __popc(m & ((1u << lane) - 1u))] = appendSlot;
+      }
+    }
+  }
+  flush_counters(t.counters, 0u, 0u, Counters{0u, 0u}, nSamples, nEscaped);
+}
+
+// rgb += colour_s (+ throughput_s * env_s when an environment light is loaded), s in chunk order.
+__global__ void wf_accumulate_kernel(float* rays, uint32_t numRays, uint32_t chunk, const float* slotColor,
+                                     const float* slotEscape, const float* slotEnv) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= numRays) return;
+  float* tr = rays + (size_t)idx * TR_WORDS;
+  V3 rgb = mk(tr[TR_RGB], tr[TR_RGB + 1], tr[TR_RGB + 2]);
+  for (uint32_t c = 0; c < chunk; ++c) {
+    const size_t slot = (size_t)idx * chunk + c;
+    const float* col = slotColor + 3 * slot;
+    rgb = rgb + mk(col[0], col[1], col[2]);
+    if (slotEnv) {
+      const float* se = slotEscape + 5 * slot;
+      if (se[3] >= 0.f) {
+        const float* env = slotEnv + 3 * slot;
+        rgb = rgb + mk(se[0], se[1], se[2]) * mk(env[2], env[1], env[0]);
+      }
+    }
+  }
+  tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z;
+}
+
+}  // namespace rt

@@ -9,7 +9,7 @@ from ipu_ray_lib_b200 import _capi as capi, scene
 pytestmark = pytest.mark.gpu
 
 # (traversal, scene_residency): reference order / near-first / near-first state machine x smem-staged / L2-resident BVH
-VARIANTS = [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2)]
+VARIANTS = [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (4, 1), (4, 2)]  # 4 = wavefront (HBM-streamed) path tracer
 
 
 @pytest.fixture(scope="module")
