@@ -1,8 +1,725 @@
-// importScene placeholder; the COLLADA/GLB-with-camera importer lands in scene_import.cpp (N2).
+// importScene: whole-scene loader with camera and material interpretation (src/scene_utils.cpp:151-317).
+//
+// The reference delegates file parsing to assimp (un-vendored dependency; flags PreTransformVertices |
+// OptimizeMeshes | CalcTangentSpace | Triangulate | JoinIdenticalVertices | SortByPType, :155-161). This
+// file restates the part of that pipeline the two shipped scenes need -- COLLADA 1.4.1 as Blender writes it:
+//   * <library_cameras>/<perspective>/<xfov>, placed by a <node><matrix> in the visual scene,
+//   * <library_effects> lambert/phong/blinn blocks: emission, diffuse, index_of_refraction, reflectivity, shininess,
+//   * <library_geometries>: <mesh> with <source> float arrays and <triangles>/<polylist> primitives whose index
+//     tuples carry VERTEX (+ NORMAL, + anything else, skipped) offsets,
+//   * <library_visual_scenes>: nested <node> with <matrix>/<translate>/<rotate>/<scale> and <instance_geometry>
+//     bound to materials through <instance_material symbol= target=>.
+// What assimp then does, and is mirrored here:
+//   PreTransformVertices  -> node world matrices are baked into positions (and the inverse transpose into normals,
+//                            renormalised); every instance sharing a material lands in ONE output mesh, output meshes
+//                            ascend by material index (same rule as gltf_import.cpp),
+//   JoinIdenticalVertices -> vertices with identical (position, normal) VALUES are merged, first occurrence keeps
+//                            its slot, so a mesh holds <= 65536 vertices for the u16 `Triangle` (Primitives.hpp:21-25),
+//   aiCamera::GetCameraMatrix -> rows x = up^look, y = up, z = look with the translation -(axis . position).
+// COLLADA's up_axis only adds one rigid transform to the root which cancels when everything is moved into camera
+// space below, so it is not applied. The material heuristics (emissive, shininess-as-emission-factor, "glass" in the
+// name, reflectivity > 0) and the final camera-space map with the x/z handedness flip follow :207-314 step by step.
+// assimp's exact vertex order cannot be checked here: geometry-level parity with a reference build is unpinned
+// (SURVEY.md appendix D); trace parity is defined on the arrays this loader emits, fed to oracle and GPU alike.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
 #include <stdexcept>
+#include <unordered_map>
+
 #include "scene_build.hpp"
+
 namespace b200rt {
-SceneParts importScene(const std::string& file, bool) {
-  throw std::runtime_error("importScene: no importer for '" + file + "' yet");
+
+std::vector<MeshParts> readGlbMeshes(const std::string& file, bool loadNormals);  // gltf_import.cpp
+
+namespace {
+
+// ---------------------------------------------------------------- XML (elements, attributes, text)
+struct XmlNode {
+  std::string tag;
+  std::vector<std::pair<std::string, std::string>> attrs;
+  std::string text;
+  std::vector<std::unique_ptr<XmlNode>> kids;
+
+  const std::string* attr(const char* name) const {
+    for (const auto& a : attrs) if (a.first == name) return &a.second;
+    return nullptr;
+  }
+  std::string attrOr(const char* name, const std::string& dflt = "") const {
+    const std::string* a = attr(name);
+    return a ? *a : dflt;
+  }
+  const XmlNode* child(const char* name) const {
+    for (const auto& k : kids) if (k->tag == name) return k.get();
+    return nullptr;
+  }
+  std::vector<const XmlNode*> children(const char* name) const {
+    std::vector<const XmlNode*> out;
+    for (const auto& k : kids) if (k->tag == name) out.push_back(k.get());
+    return out;
+  }
+  // a/b/c path lookup, first match at every level
+  const XmlNode* path(const char* p) const {
+    const XmlNode* n = this;
+    std::string part;
+    for (const char* c = p;; ++c) {
+      if (*c == '/' || *c == 0) {
+        n = n->child(part.c_str());
+        if (!n || *c == 0) return n;
+        part.clear();
+      } else {
+        part.push_back(*c);
+      }
+    }
+  }
+};
+
+class XmlParser {
+ public:
+  explicit XmlParser(const std::string& s) : s_(s) {}
+
+  std::unique_ptr<XmlNode> parseDocument() {
+    skipMisc();
+    auto root = parseElement();
+    if (!root) fail("no root element");
+    return root;
+  }
+
+ private:
+  const std::string& s_;
+  size_t i_ = 0;
+
+  [[noreturn]] void fail(const std::string& what) const {
+    throw std::runtime_error("XML parse error at byte " + std::to_string(i_) + ": " + what);
+  }
+  bool startsWith(const char* lit) const { return s_.compare(i_, std::strlen(lit), lit) == 0; }
+  void skipSpace() { while (i_ < s_.size() && std::isspace((unsigned char)s_[i_])) ++i_; }
+  void skipUntil(const char* end) {
+    const size_t p = s_.find(end, i_);
+    if (p == std::string::npos) fail(std::string("unterminated construct, expected ") + end);
+    i_ = p + std::strlen(end);
+  }
+  // comments, processing instructions, doctype
+  void skipMisc() {
+    for (;;) {
+      skipSpace();
+      if (startsWith("<!--")) skipUntil("-->");
+      else if (startsWith("<?")) skipUntil("?>");
+      else if (startsWith("<!")) skipUntil(">");
+      else return;
+    }
+  }
+  static std::string decode(const std::string& in) {
+    if (in.find('&') == std::string::npos) return in;
+    static const std::pair<const char*, char> ents[] = {{"&lt;", '<'}, {"&gt;", '>'}, {"&amp;", '&'}, {"&quot;", '"'}, {"&apos;", '\''}};
+    std::string out;
+    for (size_t i = 0; i < in.size();) {
+      bool hit = false;
+      if (in[i] == '&')
+        for (const auto& e : ents) {
+          const size_t n = std::strlen(e.first);
+          if (in.compare(i, n, e.first) == 0) { out.push_back(e.second); i += n; hit = true; break; }
+        }
+      if (!hit) out.push_back(in[i++]);
+    }
+    return out;
+  }
+  std::string parseName() {
+    const size_t b = i_;
+    while (i_ < s_.size() && !std::isspace((unsigned char)s_[i_]) && s_[i_] != '>' && s_[i_] != '/' && s_[i_] != '=') ++i_;
+    if (i_ == b) fail("expected a name");
+    return s_.substr(b, i_ - b);
+  }
+  std::unique_ptr<XmlNode> parseElement() {
+    if (i_ >= s_.size() || s_[i_] != '<') return nullptr;
+    ++i_;
+    auto n = std::make_unique<XmlNode>();
+    n->tag = parseName();
+    for (;;) {
+      skipSpace();
+      if (i_ >= s_.size()) fail("unterminated tag <" + n->tag);
+      if (s_[i_] == '/') {
+        if (i_ + 1 >= s_.size() || s_[i_ + 1] != '>') fail("malformed empty-element tag");
+        i_ += 2;
+        return n;
+      }
+      if (s_[i_] == '>') { ++i_; break; }
+      std::string key = parseName();
+      skipSpace();
+      if (i_ >= s_.size() || s_[i_] != '=') fail("attribute without value");
+      ++i_;
+      skipSpace();
+      if (i_ >= s_.size() || (s_[i_] != '"' && s_[i_] != '\'')) fail("unquoted attribute value");
+      const char q = s_[i_++];
+      const size_t e = s_.find(q, i_);
+      if (e == std::string::npos) fail("unterminated attribute value");
+      n->attrs.emplace_back(std::move(key), decode(s_.substr(i_, e - i_)));
+      i_ = e + 1;
+    }
+    // content
+    for (;;) {
+      const size_t lt = s_.find('<', i_);
+      if (lt == std::string::npos) fail("missing </" + n->tag + ">");
+      if (lt > i_) n->text.append(s_, i_, lt - i_);
+      i_ = lt;
+      if (startsWith("</")) {
+        i_ += 2;
+        const std::string close = parseName();
+        if (close != n->tag) fail("</" + close + "> closes <" + n->tag + ">");
+        skipSpace();
+        if (i_ >= s_.size() || s_[i_] != '>') fail("malformed end tag");
+        ++i_;
+        n->text = decode(n->text);
+        return n;
+      }
+      if (startsWith("<!--")) { skipUntil("-->"); continue; }
+      if (startsWith("<![CDATA[")) {
+        const size_t b = i_ + 9;
+        skipUntil("]]>");
+        n->text.append(s_, b, i_ - 3 - b);
+        continue;
+      }
+      if (startsWith("<?")) { skipUntil("?>"); continue; }
+      n->kids.push_back(parseElement());
+    }
+  }
+};
+
+// ---------------------------------------------------------------- number lists
+template <class T, class Conv>
+std::vector<T> parseList(const std::string& text, Conv conv) {
+  std::vector<T> out;
+  const char* p = text.c_str();
+  for (;;) {
+    while (*p && std::isspace((unsigned char)*p)) ++p;
+    if (!*p) break;
+    char* end = nullptr;
+    const T v = conv(p, &end);
+    if (end == p) throw std::runtime_error(std::string("COLLADA: bad number near '") + std::string(p).substr(0, 16) + "'");
+    out.push_back(v);
+    p = end;
+  }
+  return out;
 }
+std::vector<float> parseFloats(const std::string& t) {
+  return parseList<float>(t, [](const char* p, char** e) { return std::strtof(p, e); });
+}
+std::vector<long> parseInts(const std::string& t) {
+  return parseList<long>(t, [](const char* p, char** e) { return std::strtol(p, e, 10); });
+}
+
+// ---------------------------------------------------------------- 4x4 maths (float, like assimp's ai_real)
+struct M4 {
+  float m[4][4];
+  static M4 identity() {
+    M4 r{};
+    for (int i = 0; i < 4; ++i) r.m[i][i] = 1.f;
+    return r;
+  }
+  M4 operator*(const M4& o) const {
+    M4 r{};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+        for (int k = 0; k < 4; ++k) s += m[i][k] * o.m[k][j];
+        r.m[i][j] = s;
+      }
+    return r;
+  }
+  Vec3 point(const Vec3& p) const {
+    return Vec3{m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3],
+                m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3],
+                m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3]};
+  }
+  Vec3 dir(const Vec3& p) const {
+    return Vec3{m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z, m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z,
+                m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z};
+  }
+};
+
+struct M3 { float m[3][3]; };
+
+// inverse transpose of the upper 3x3 (cofactor matrix / det), the map for normals
+M3 normalMatrix(const M4& w) {
+  const float a = w.m[0][0], b = w.m[0][1], c = w.m[0][2];
+  const float d = w.m[1][0], e = w.m[1][1], f = w.m[1][2];
+  const float g = w.m[2][0], h = w.m[2][1], i = w.m[2][2];
+  const float C[3][3] = {{e * i - f * h, f * g - d * i, d * h - e * g},
+                         {c * h - b * i, a * i - c * g, b * g - a * h},
+                         {b * f - c * e, c * d - a * f, a * e - b * d}};
+  const float det = a * C[0][0] + b * C[0][1] + c * C[0][2];
+  if (det == 0.f) throw std::runtime_error("COLLADA: singular node transform");
+  M3 r;
+  for (int y = 0; y < 3; ++y) for (int x = 0; x < 3; ++x) r.m[y][x] = C[y][x] / det;
+  return r;
+}
+Vec3 mul(const M3& m, const Vec3& v) {
+  return Vec3{m.m[0][0] * v.x + m.m[0][1] * v.y + m.m[0][2] * v.z, m.m[1][0] * v.x + m.m[1][1] * v.y + m.m[1][2] * v.z,
+              m.m[2][0] * v.x + m.m[2][1] * v.y + m.m[2][2] * v.z};
+}
+Vec3 normalised(const Vec3& v) {
+  const float l = std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+  return l > 0.f ? Vec3{v.x / l, v.y / l, v.z / l} : v;
+}
+Vec3 cross(const Vec3& a, const Vec3& b) {
+  return Vec3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+float dot(const Vec3& a, const Vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// One <node>'s local transform: its transform elements composed in document order.
+M4 nodeLocal(const XmlNode& node) {
+  M4 M = M4::identity();
+  for (const auto& k : node.kids) {
+    M4 T = M4::identity();
+    if (k->tag == "matrix") {
+      const auto v = parseFloats(k->text);
+      if (v.size() != 16) throw std::runtime_error("COLLADA: <matrix> needs 16 values");
+      for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T.m[r][c] = v[(size_t)(r * 4 + c)];  // row-major
+    } else if (k->tag == "translate") {
+      const auto v = parseFloats(k->text);
+      if (v.size() != 3) throw std::runtime_error("COLLADA: <translate> needs 3 values");
+      T.m[0][3] = v[0]; T.m[1][3] = v[1]; T.m[2][3] = v[2];
+    } else if (k->tag == "scale") {
+      const auto v = parseFloats(k->text);
+      if (v.size() != 3) throw std::runtime_error("COLLADA: <scale> needs 3 values");
+      T.m[0][0] = v[0]; T.m[1][1] = v[1]; T.m[2][2] = v[2];
+    } else if (k->tag == "rotate") {
+      const auto v = parseFloats(k->text);
+      if (v.size() != 4) throw std::runtime_error("COLLADA: <rotate> needs 4 values");
+      const Vec3 ax = normalised(Vec3{v[0], v[1], v[2]});
+      const float ang = v[3] * 3.14159265358979323846f / 180.f;
+      const float c = std::cos(ang), s = std::sin(ang), t = 1.f - c;
+      const float R[3][3] = {{t * ax.x * ax.x + c, t * ax.x * ax.y - s * ax.z, t * ax.x * ax.z + s * ax.y},
+                             {t * ax.x * ax.y + s * ax.z, t * ax.y * ax.y + c, t * ax.y * ax.z - s * ax.x},
+                             {t * ax.x * ax.z - s * ax.y, t * ax.y * ax.z + s * ax.x, t * ax.z * ax.z + c}};
+      for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) T.m[r][cc] = R[r][cc];
+    } else {
+      continue;
+    }
+    M = M * T;
+  }
+  return M;
+}
+
+std::string stripHash(const std::string& url) { return (!url.empty() && url[0] == '#') ? url.substr(1) : url; }
+
+// ---------------------------------------------------------------- COLLADA document model
+struct Source {
+  std::vector<float> data;
+  size_t stride = 3, offset = 0, count = 0;
+  Vec3 get3(size_t i) const {
+    if (i >= count) throw std::runtime_error("COLLADA: index beyond <source> count");
+    const size_t b = offset + i * stride;
+    return Vec3{data.at(b), data.at(b + 1), data.at(b + 2)};
+  }
+};
+
+struct Primitive {           // one <triangles>/<polylist>/<polygons> block, already triangulated
+  std::string materialSymbol;
+  std::vector<std::uint32_t> posIdx, nrmIdx;  // three per triangle; nrmIdx empty when the block has no NORMAL input
+  const Source* positions = nullptr;
+  const Source* normals = nullptr;
+};
+
+struct Geometry { std::vector<Primitive> prims; };
+
+struct Collada {
+  std::unique_ptr<XmlNode> root;
+  std::map<std::string, Source> sources;                       // id -> float source
+  std::map<std::string, std::string> verticesToPositionSource;  // <vertices id> -> POSITION source id
+  std::map<std::string, std::string> verticesToNormalSource;    // <vertices id> -> NORMAL source id (rare)
+  std::map<std::string, Geometry> geometries;
+  std::vector<std::string> materialIds;                         // <library_materials> order = material index
+  std::map<std::string, size_t> materialIndex;
+  std::vector<Material> materials;
+};
+
+void readSource(const XmlNode& src, Collada& doc) {
+  const XmlNode* fa = src.child("float_array");
+  if (!fa) return;  // Name_array etc.: nothing the trace path reads
+  Source s;
+  s.data = parseFloats(fa->text);
+  if (const XmlNode* acc = src.path("technique_common/accessor")) {
+    s.stride = (size_t)std::stoul(acc->attrOr("stride", "1"));
+    s.offset = (size_t)std::stoul(acc->attrOr("offset", "0"));
+    s.count = (size_t)std::stoul(acc->attrOr("count", "0"));
+  } else {
+    s.count = s.data.size() / 3;
+  }
+  doc.sources[src.attrOr("id")] = std::move(s);
+}
+
+void readGeometry(const XmlNode& geom, Collada& doc) {
+  const XmlNode* mesh = geom.child("mesh");
+  if (!mesh) return;  // splines / convex meshes are not renderable here
+  for (const XmlNode* s : mesh->children("source")) readSource(*s, doc);
+  for (const XmlNode* v : mesh->children("vertices"))
+    for (const XmlNode* in : v->children("input")) {
+      const std::string sem = in->attrOr("semantic");
+      if (sem == "POSITION") doc.verticesToPositionSource[v->attrOr("id")] = stripHash(in->attrOr("source"));
+      if (sem == "NORMAL") doc.verticesToNormalSource[v->attrOr("id")] = stripHash(in->attrOr("source"));
+    }
+
+  Geometry g;
+  for (const auto& k : mesh->kids) {
+    const bool tri = k->tag == "triangles", plist = k->tag == "polylist", pgons = k->tag == "polygons";
+    if (!tri && !plist && !pgons) {
+      // SortByPType + the reference's "only triangle meshes" rule: lines/points never reach the scene.
+      continue;
+    }
+    Primitive p;
+    p.materialSymbol = k->attrOr("material");
+    size_t tupleSize = 0;
+    long vertexOff = -1, normalOff = -1;
+    std::string vertexSrc, normalSrc;
+    for (const XmlNode* in : k->children("input")) {
+      const size_t off = (size_t)std::stoul(in->attrOr("offset", "0"));
+      tupleSize = std::max(tupleSize, off + 1);
+      const std::string sem = in->attrOr("semantic");
+      if (sem == "VERTEX") { vertexOff = (long)off; vertexSrc = stripHash(in->attrOr("source")); }
+      if (sem == "NORMAL") { normalOff = (long)off; normalSrc = stripHash(in->attrOr("source")); }
+    }
+    if (vertexOff < 0) throw std::runtime_error("COLLADA: primitive block without a VERTEX input");
+    auto posIt = doc.verticesToPositionSource.find(vertexSrc);
+    if (posIt == doc.verticesToPositionSource.end()) throw std::runtime_error("COLLADA: unknown <vertices> '" + vertexSrc + "'");
+    auto ps = doc.sources.find(posIt->second);
+    if (ps == doc.sources.end()) throw std::runtime_error("COLLADA: unknown position source '" + posIt->second + "'");
+    p.positions = &ps->second;
+    bool normalsFollowVertex = false;
+    if (normalOff < 0) {
+      auto nIt = doc.verticesToNormalSource.find(vertexSrc);
+      if (nIt != doc.verticesToNormalSource.end()) { normalSrc = nIt->second; normalsFollowVertex = true; }
+    }
+    if (!normalSrc.empty()) {
+      auto ns = doc.sources.find(normalSrc);
+      if (ns == doc.sources.end()) throw std::runtime_error("COLLADA: unknown normal source '" + normalSrc + "'");
+      p.normals = &ns->second;
+    }
+
+    // Gather polygons as runs of index tuples, then fan-triangulate (aiProcess_Triangulate).
+    std::vector<std::vector<long>> polys;  // flattened tuples per polygon
+    if (pgons) {
+      for (const XmlNode* pe : k->children("p")) polys.push_back(parseInts(pe->text));
+    } else {
+      const XmlNode* pe = k->child("p");
+      const std::vector<long> idx = pe ? parseInts(pe->text) : std::vector<long>();
+      if (tri) {
+        if (idx.size() % (3 * tupleSize)) throw std::runtime_error("COLLADA: <triangles> index count is not a multiple of 3 tuples");
+        for (size_t b = 0; b < idx.size(); b += 3 * tupleSize) polys.emplace_back(idx.begin() + (long)b, idx.begin() + (long)(b + 3 * tupleSize));
+      } else {
+        const XmlNode* vc = k->child("vcount");
+        if (!vc) throw std::runtime_error("COLLADA: <polylist> without <vcount>");
+        size_t b = 0;
+        for (long n : parseInts(vc->text)) {
+          const size_t len = (size_t)n * tupleSize;
+          if (n < 0 || b + len > idx.size()) throw std::runtime_error("COLLADA: <polylist> indices shorter than <vcount> says");
+          polys.emplace_back(idx.begin() + (long)b, idx.begin() + (long)(b + len));
+          b += len;
+        }
+      }
+    }
+    for (const auto& poly : polys) {
+      const size_t n = poly.size() / tupleSize;
+      if (n < 3) continue;  // degenerate faces are dropped with the point/line primitives
+      auto corner = [&](size_t c, std::uint32_t& pi, std::uint32_t& ni) {
+        const long v = poly[c * tupleSize + (size_t)vertexOff];
+        if (v < 0) throw std::runtime_error("COLLADA: negative index");
+        pi = (std::uint32_t)v;
+        ni = normalsFollowVertex ? pi : (normalOff >= 0 ? (std::uint32_t)poly[c * tupleSize + (size_t)normalOff] : 0u);
+      };
+      for (size_t c = 1; c + 1 < n; ++c) {
+        const size_t cs[3] = {0, c, c + 1};
+        for (size_t cc : cs) {
+          std::uint32_t pi, ni;
+          corner(cc, pi, ni);
+          p.posIdx.push_back(pi);
+          if (p.normals) p.nrmIdx.push_back(ni);
+        }
+      }
+    }
+    g.prims.push_back(std::move(p));
+  }
+  doc.geometries[geom.attrOr("id")] = std::move(g);
+}
+
+// First <float> / <color> under effect parameter `name`, if present.
+const XmlNode* shaderParam(const XmlNode& shader, const char* name, const char* kind) {
+  const XmlNode* p = shader.child(name);
+  return p ? p->child(kind) : nullptr;
+}
+
+// Effect -> Material following src/scene_utils.cpp:207-283. `name` is the material's display name (aiMaterial name).
+Material interpretEffect(const XmlNode* effect, const std::string& name) {
+  Material mat;
+  std::memset(&mat, 0, sizeof(mat));
+  mat.ior = 1.52f;  // Material() default (include/Material.hpp:13-19), kept when the importer reports none
+  mat.type = MAT_DIFFUSE;
+
+  const XmlNode* shader = nullptr;
+  if (effect)
+    if (const XmlNode* tech = effect->path("profile_COMMON/technique"))
+      for (const char* s : {"lambert", "phong", "blinn", "constant"})
+        if ((shader = tech->child(s))) break;
+
+  // assimp's Collada effect defaults (diffuse 0.6 grey, no emission, shininess 10, ior 1, reflectivity 0) stand in
+  // for parameters the file leaves out; every property below is therefore always "found" like with assimp.
+  Vec3 diffuse{0.6f, 0.6f, 0.6f}, emission{0.f, 0.f, 0.f};
+  float ior = 1.f, shininess = 10.f, reflectivity = 0.f;
+  if (shader) {
+    auto colour = [&](const char* pname, Vec3& out) {
+      if (const XmlNode* c = shaderParam(*shader, pname, "color")) {
+        const auto v = parseFloats(c->text);
+        if (v.size() >= 3) out = Vec3{v[0], v[1], v[2]};
+      }
+    };
+    auto scalar = [&](const char* pname, float& out) {
+      if (const XmlNode* f = shaderParam(*shader, pname, "float")) {
+        const auto v = parseFloats(f->text);
+        if (!v.empty()) out = v[0];
+      }
+    };
+    colour("diffuse", diffuse);
+    colour("emission", emission);
+    scalar("index_of_refraction", ior);
+    scalar("shininess", shininess);
+    scalar("reflectivity", reflectivity);
+  }
+
+  mat.albedo = diffuse;                                               // :222-227
+  mat.emission = emission;                                            // :229-238
+  mat.emissive = (emission.x != 0.f || emission.y != 0.f || emission.z != 0.f) ? 1 : 0;
+  mat.ior = ior;                                                      // :240-243
+  if (mat.emissive) {                                                 // :249-258 shininess doubles as emission factor
+    mat.emission.x *= shininess; mat.emission.y *= shininess; mat.emission.z *= shininess;
+  }
+  // :260-268 transparency factor: assimp's COLLADA reader publishes opacity, not a transparency factor, so that
+  // branch never fires for these files; the name rule below is the reference's own stand-in.
+  if (name.find("glass") != std::string::npos) mat.type = MAT_REFRACTIVE;  // :270-273
+  if (reflectivity > 0.f) mat.type = MAT_SPECULAR;                          // :275-283
+  return mat;
+}
+
+struct CameraPose {
+  bool found = false;
+  float xfovDegrees = 45.f;
+  M4 world = M4::identity();
+};
+
+struct Instance {  // one <instance_geometry> with its baked world matrix
+  const Geometry* geom;
+  M4 world;
+  std::map<std::string, std::string> symbolToTarget;
+};
+
+void walkNodes(const XmlNode& node, const M4& parent, const Collada& doc, const std::map<std::string, const XmlNode*>& cameras,
+               std::vector<Instance>& instances, CameraPose& cam) {
+  const M4 world = parent * nodeLocal(node);
+  for (const auto& k : node.kids) {
+    if (k->tag == "instance_geometry") {
+      auto g = doc.geometries.find(stripHash(k->attrOr("url")));
+      if (g == doc.geometries.end()) continue;
+      Instance inst{&g->second, world, {}};
+      if (const XmlNode* tc = k->path("bind_material/technique_common"))
+        for (const XmlNode* im : tc->children("instance_material"))
+          inst.symbolToTarget[im->attrOr("symbol")] = stripHash(im->attrOr("target"));
+      instances.push_back(std::move(inst));
+    } else if (k->tag == "instance_camera" && !cam.found) {
+      auto c = cameras.find(stripHash(k->attrOr("url")));
+      if (c == cameras.end()) continue;
+      cam.found = true;
+      cam.world = world;
+      if (const XmlNode* persp = c->second->path("optics/technique_common/perspective")) {
+        const XmlNode* xf = persp->child("xfov");
+        const XmlNode* yf = persp->child("yfov");
+        const XmlNode* ar = persp->child("aspect_ratio");
+        if (xf) {
+          cam.xfovDegrees = parseFloats(xf->text).at(0);
+        } else if (yf) {  // assimp derives the horizontal angle from yfov and the aspect ratio
+          const float y = parseFloats(yf->text).at(0) * 3.14159265358979323846f / 180.f;
+          const float a = ar ? parseFloats(ar->text).at(0) : 1.f;
+          cam.xfovDegrees = 2.f * std::atan(a * std::tan(.5f * y)) * 180.f / 3.14159265358979323846f;
+        }
+      }
+    } else if (k->tag == "node") {
+      walkNodes(*k, world, doc, cameras, instances, cam);
+    }
+  }
+}
+
+struct VertexKey {
+  std::uint32_t bits[6];
+  bool operator==(const VertexKey& o) const { return std::memcmp(bits, o.bits, sizeof(bits)) == 0; }
+};
+struct VertexKeyHash {
+  size_t operator()(const VertexKey& k) const {
+    std::uint64_t h = 1469598103934665603ull;
+    for (std::uint32_t b : k.bits) { h ^= b; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+
+SceneParts importCollada(const std::string& file, bool loadNormals) {
+  std::ifstream in(file, std::ios::binary);
+  if (!in) throw std::runtime_error("Could not load scene file.");
+  std::stringstream ss;
+  ss << in.rdbuf();
+  const std::string text = ss.str();
+
+  Collada doc;
+  doc.root = XmlParser(text).parseDocument();
+  if (doc.root->tag != "COLLADA") throw std::runtime_error("Could not load scene file.");
+
+  // cameras
+  std::map<std::string, const XmlNode*> cameras;
+  for (const XmlNode* lib : doc.root->children("library_cameras"))
+    for (const XmlNode* c : lib->children("camera")) cameras[c->attrOr("id")] = c;
+  if (cameras.empty()) throw std::runtime_error("No camera found in scene file.");  // :176-180
+
+  // effects and materials (material index = order in <library_materials>)
+  std::map<std::string, const XmlNode*> effects;
+  for (const XmlNode* lib : doc.root->children("library_effects"))
+    for (const XmlNode* e : lib->children("effect")) effects[e->attrOr("id")] = e;
+  for (const XmlNode* lib : doc.root->children("library_materials"))
+    for (const XmlNode* m : lib->children("material")) {
+      const std::string id = m->attrOr("id");
+      const XmlNode* ie = m->child("instance_effect");
+      const XmlNode* eff = nullptr;
+      if (ie) {
+        auto it = effects.find(stripHash(ie->attrOr("url")));
+        if (it != effects.end()) eff = it->second;
+      }
+      doc.materialIndex[id] = doc.materialIds.size();
+      doc.materialIds.push_back(id);
+      doc.materials.push_back(interpretEffect(eff, m->attrOr("name", id)));
+    }
+
+  for (const XmlNode* lib : doc.root->children("library_geometries"))
+    for (const XmlNode* g : lib->children("geometry")) readGeometry(*g, doc);
+
+  // the instantiated visual scene
+  const XmlNode* vscene = nullptr;
+  std::string wanted;
+  if (const XmlNode* inst = doc.root->path("scene/instance_visual_scene")) wanted = stripHash(inst->attrOr("url"));
+  for (const XmlNode* lib : doc.root->children("library_visual_scenes"))
+    for (const XmlNode* v : lib->children("visual_scene"))
+      if (!vscene || v->attrOr("id") == wanted) vscene = v;
+  if (!vscene) throw std::runtime_error("Could not load scene file.");
+
+  std::vector<Instance> instances;
+  CameraPose cam;
+  for (const XmlNode* n : vscene->children("node")) walkNodes(*n, M4::identity(), doc, cameras, instances, cam);
+  if (!cam.found) throw std::runtime_error("No camera found in scene file.");
+
+  // Bake instances into one mesh per material, joining identical vertices.
+  struct Builder {
+    MeshParts mesh;
+    std::unordered_map<VertexKey, std::uint32_t, VertexKeyHash> lookup;
+  };
+  std::map<size_t, Builder> byMaterial;
+  bool needDefaultMaterial = false;
+  const size_t defaultMaterial = doc.materials.size();
+  for (const Instance& inst : instances) {
+    const M3 nm = normalMatrix(inst.world);
+    for (const Primitive& p : inst.geom->prims) {
+      size_t matIdx = defaultMaterial;
+      auto bound = inst.symbolToTarget.find(p.materialSymbol);
+      auto mi = doc.materialIndex.find(bound != inst.symbolToTarget.end() ? bound->second : p.materialSymbol);
+      if (mi != doc.materialIndex.end()) matIdx = mi->second; else needDefaultMaterial = true;
+      Builder& b = byMaterial[matIdx];
+      const bool hasN = p.normals != nullptr;
+      for (size_t c = 0; c + 2 < p.posIdx.size(); c += 3) {
+        std::uint16_t tri[3];
+        for (int k = 0; k < 3; ++k) {
+          const Vec3 pos = inst.world.point(p.positions->get3(p.posIdx[c + (size_t)k]));
+          Vec3 nrm{0.f, 0.f, 0.f};
+          if (hasN) nrm = normalised(mul(nm, p.normals->get3(p.nrmIdx[c + (size_t)k])));
+          VertexKey key;
+          std::memcpy(key.bits, &pos, 12);
+          std::memcpy(key.bits + 3, &nrm, 12);
+          auto found = b.lookup.find(key);
+          std::uint32_t slot;
+          if (found != b.lookup.end()) {
+            slot = found->second;
+          } else {
+            slot = (std::uint32_t)b.mesh.vertices.size();
+            if (slot > 65535u)
+              throw std::runtime_error("Mesh has more than 65536 vertices: too many for 16-bit triangle indices.");
+            b.lookup.emplace(key, slot);
+            b.mesh.vertices.push_back(pos);
+            b.mesh.normals.push_back(nrm);
+          }
+          tri[k] = (std::uint16_t)slot;
+        }
+        b.mesh.triangles.push_back(Triangle{tri[0], tri[1], tri[2]});
+      }
+    }
+  }
+
+  SceneParts scene;
+  scene.materials = doc.materials;
+  if (needDefaultMaterial) scene.materials.push_back(interpretEffect(nullptr, "DefaultMaterial"));
+  for (auto& kv : byMaterial) {
+    if (kv.second.mesh.triangles.empty()) continue;
+    bool anyNormal = false;
+    for (const auto& n : kv.second.mesh.normals) anyNormal |= (n.x != 0.f || n.y != 0.f || n.z != 0.f);
+    if (!loadNormals || !anyNormal) kv.second.mesh.normals.clear();  // getMeshes :87-95
+    scene.meshes.push_back(std::move(kv.second.mesh));
+    scene.matIDs.push_back((std::uint32_t)kv.first);
+  }
+  if (scene.meshes.empty()) throw std::runtime_error("Could not load scene file.");
+
+  // Camera: position/look/up carried through the node matrix, then aiCamera::GetCameraMatrix.
+  scene.horizontalFov = cam.xfovDegrees * 3.14159265358979323846f / 180.f;  // full horizontal angle (app_utils.cpp:27-28)
+  const Vec3 position = cam.world.point(Vec3{0.f, 0.f, 0.f});
+  const Vec3 look = normalised(cam.world.dir(Vec3{0.f, 0.f, -1.f}));
+  const Vec3 up = normalised(cam.world.dir(Vec3{0.f, 1.f, 0.f}));
+  const Vec3 xaxis = normalised(cross(up, look));
+  M4 cm = M4::identity();
+  const Vec3 axes[3] = {xaxis, up, look};
+  for (int r = 0; r < 3; ++r) {
+    cm.m[r][0] = axes[r].x; cm.m[r][1] = axes[r].y; cm.m[r][2] = axes[r].z;
+    cm.m[r][3] = -dot(axes[r], position);
+  }
+
+  // :286-314 everything into camera space, then swap handedness. The matrix is orthonormal, so the rotation assimp
+  // extracts from its inverse transpose is its own upper 3x3.
+  for (auto& m : scene.meshes) {
+    for (auto& v : m.vertices) {
+      const Vec3 p = cm.point(v);
+      v = Vec3{-p.x, p.y, -p.z};
+    }
+    for (auto& n : m.normals) {
+      const Vec3 p = cm.dir(n);
+      n = Vec3{-p.x, p.y, -p.z};
+    }
+  }
+  return scene;
+}
+
+bool endsWithNoCase(const std::string& s, const char* suffix) {
+  const size_t n = std::strlen(suffix);
+  if (s.size() < n) return false;
+  for (size_t i = 0; i < n; ++i)
+    if (std::tolower((unsigned char)s[s.size() - n + i]) != suffix[i]) return false;
+  return true;
+}
+
+}  // namespace
+
+SceneParts importScene(const std::string& file, bool loadNormals) {
+  if (endsWithNoCase(file, ".dae")) return importCollada(file, loadNormals);
+  if (endsWithNoCase(file, ".glb")) {
+    // The binary glTF reader handles meshes only; this build's one .glb asset has no camera, which the
+    // reference rejects as well (src/scene_utils.cpp:176-180).
+    (void)readGlbMeshes(file, loadNormals);  // surfaces "cannot read" before "no camera", like assimp would
+    throw std::runtime_error("No camera found in scene file.");
+  }
+  throw std::runtime_error("Could not load scene file.");
+}
+
 }  // namespace b200rt

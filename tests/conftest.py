@@ -78,3 +78,19 @@ def assert_streams_identical(a, b, what=""):
     per_word = {WORD_NAMES[i]: int(c) for i, c in enumerate((wa != wb).sum(axis=0)) if c}
     raise AssertionError(f"{what}: {bad.size}/{a.size} rays differ; per field {per_word}; first {bad[:5]}\n"
                          f"a={a[bad[0]]}\nb={b[bad[0]]}")
+
+
+@pytest.fixture(scope="session")
+def dae_scene():
+    """assets/test_scene.dae with interpolated normals (BASELINE.json config 3)."""
+    from ipu_ray_lib_b200 import HostScene
+
+    return HostScene.from_file(ROOT / "assets" / "test_scene.dae", load_normals=True)
+
+
+@pytest.fixture(scope="session")
+def hdri_scene():
+    """assets/hdri_test.dae, open sky (BASELINE.json config 5)."""
+    from ipu_ray_lib_b200 import HostScene
+
+    return HostScene.from_file(ROOT / "assets" / "hdri_test.dae", load_normals=False)

@@ -58,6 +58,36 @@ def test_path_trace_bit_exact_all_variants(B200Scene, port, name):
                 assert st["node_visits"] == cw["node_visits"] and st["prim_tests"] == cw["prim_tests"]
 
 
+@pytest.mark.parametrize("fixture,normals", [("dae_scene", True), ("hdri_scene", False)])
+def test_imported_collada_scenes_bit_exact(B200Scene, port, fixture, normals, request):
+    """BASELINE.json configs 3 and 5 at test size: imported triangle scenes (406 KB / 271 KB of BVH: the first does not
+    fit shared memory, so residency 1 falls back to L2), glass + mirrors + emitters, interpolated normals."""
+    s = request.getfixturevalue(fixture)
+    assert (s.mesh_normals.size > 0) == normals
+    w, h, spp = 112, 96, 6
+    s.configure(w, h, path_trace=True, samples=spp, seed=99)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    cw = port.path_trace(s, want)
+    assert cw["escaped_samples"] > 0 and cw["closest_hit_queries"] > 2 * w * h
+    with B200Scene(s) as g:
+        for trav, res in VARIANTS:
+            got = base.copy()
+            g.execute(got, traversal=trav, scene_residency=res, count_visits=1)
+            assert_streams_identical(got, want, f"{fixture} path trav={trav} res={res}")
+            st = g.stats()
+            for k in ("closest_hit_queries", "samples", "escaped_samples"):
+                assert st[k] == cw[k], k
+    s.configure(w, h, path_trace=False)
+    want = base.copy()
+    port.shadow_trace(s, want, light=(0.0, 6.0, -3.0))
+    with B200Scene(s) as g:
+        for trav, res in VARIANTS[:4]:
+            got = base.copy()
+            g.execute(got, light_pos=(0.0, 6.0, -3.0), traversal=trav, scene_residency=res)
+            assert_streams_identical(got, want, f"{fixture} shadow trav={trav} res={res}")
+
+
 def test_against_reference_build_when_present(B200Scene, ref):
     """Same comparison against the reference's own compiled kernels (oracle/_ref)."""
     s = scene.HostScene.builtin("box").configure(256, 256, path_trace=False)

@@ -51,7 +51,7 @@ def test_unknown_scene_is_an_error():
         scene.HostScene.builtin("nope")
 
 
-@pytest.mark.parametrize("fixture", ["box_scene", "spheres_scene"])
+@pytest.mark.parametrize("fixture", ["box_scene", "spheres_scene", "dae_scene", "hdri_scene"])
 def test_bvh_is_preorder_binary_and_conservative(fixture, request):
     s = request.getfixturevalue(fixture)
     nodes = s.bvh_nodes
