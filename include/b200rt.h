@@ -175,6 +175,13 @@ int b200rt_trace(b200rt_scene* scene, const b200rt_trace_params* params,
 int b200rt_trace_device(b200rt_scene* scene, const b200rt_trace_params* params,
                         void* d_rays, size_t n, void* stream);
 
+/* Page-lock / release a caller-owned ray stream so that b200rt_trace's copies run as DMA at PCIe speed (pageable
+ * memory works too, at a fraction of the bandwidth). The reference pins nothing itself -- Poplar's stream callbacks
+ * read the caller's vector in place (src/IpuScene.cpp:399-409, :703-707); this is the CUDA equivalent of that
+ * contract. Returns B200RT_OK, or an error the caller may ignore (tracing still works unpinned). */
+int b200rt_host_register(void* rays, size_t bytes);
+int b200rt_host_unregister(void* rays);
+
 int    b200rt_get_trace_stats(const b200rt_scene* scene, b200rt_trace_stats* out);
 /* IpuScene::getTraceTimeSecs (include/IpuScene.hpp:55). */
 double b200rt_get_trace_time_secs(const b200rt_scene* scene);

@@ -126,7 +126,7 @@ B200RT_SYMBOLS = [
     "b200rt_scene_load_nif", "b200rt_scene_set_hdri_rotation", "b200rt_scene_set_max_nif_batch_size",
     "b200rt_nif_eval", "b200rt_trace", "b200rt_trace_device",
     "b200rt_get_trace_stats", "b200rt_get_trace_time_secs",
-    "b200rt_intersect", "b200rt_occluded",
+    "b200rt_intersect", "b200rt_occluded", "b200rt_host_register", "b200rt_host_unregister",
 ]
 B200RT_SCENE_SYMBOLS = [
     "b200rt_host_scene_builtin", "b200rt_host_scene_import", "b200rt_host_scene_free",
@@ -173,6 +173,8 @@ def lib() -> C.CDLL:
         L.b200rt_get_trace_time_secs.restype = C.c_double
         L.b200rt_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32]
         L.b200rt_occluded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.b200rt_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.b200rt_host_unregister.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

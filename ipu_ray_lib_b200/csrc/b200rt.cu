@@ -708,4 +708,21 @@ int b200rt_occluded(b200rt_scene* sc, const void* raysIn, size_t n, uint8_t* out
   return B200RT_OK;
 }
 
+int b200rt_host_register(void* rays, size_t bytes) {
+  if (!rays || !bytes) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  // Portable: every device of a multi-GPU render DMA's from the same stream.
+  const cudaError_t e = cudaHostRegister(rays, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B200RT_OK; }
+  CU_TRY(e);
+  return B200RT_OK;
+}
+
+int b200rt_host_unregister(void* rays) {
+  if (!rays) return fail(B200RT_ERR_INVALID_ARG, "null argument");
+  const cudaError_t e = cudaHostUnregister(rays);
+  if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return B200RT_OK; }
+  CU_TRY(e);
+  return B200RT_OK;
+}
+
 }  // extern "C"

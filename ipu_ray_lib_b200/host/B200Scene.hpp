@@ -163,6 +163,7 @@ class B200Scene {
     auto* ctx = (CallbackCtx*)user;
     const std::size_t batchIndex = localIndex * ctx->numReplicas + ctx->replica;  // RayCallback::fetch numbering
     auto& batch = ctx->self->rayBatches_[batchIndex];
+    batch.resize(n);
     std::memcpy(batch.data(), rays, n * sizeof(TraceResult));
     (*ctx->self->rayFunc_)(batchIndex, batch);
   }
@@ -173,66 +174,83 @@ class B200Scene {
     const std::size_t R = std::max<std::uint32_t>(1, std::min<std::uint32_t>(config_.numGpus, (std::uint32_t)available));
     const std::size_t per = raysPerBatch();
     const std::size_t numBatches = (rayStream_.size() + per - 1) / per;
-    // createRayBatches (src/IpuScene.cpp:110-172) without the dud-ray padding the IPU graph needed
+    // createRayBatches (src/IpuScene.cpp:110-172) without the dud-ray padding the IPU graph needed. The per-batch
+    // vectors are only materialised for the callback, which is handed one (RayCallback::fetch).
     rayBatches_.assign(numBatches, {});
-    for (std::size_t b = 0; b < numBatches; ++b) {
-      const std::size_t lo = b * per, hi = std::min(rayStream_.size(), lo + per);
-      rayBatches_[b].assign(rayStream_.begin() + (long)lo, rayStream_.begin() + (long)hi);
-    }
-    // gather each replica's batches (i % R) into one contiguous stream so a replica fills its GPU
-    std::vector<std::vector<TraceResult>> perReplica(R);
-    for (std::size_t b = 0; b < numBatches; ++b)
-      perReplica[b % R].insert(perReplica[b % R].end(), rayBatches_[b].begin(), rayBatches_[b].end());
+    if (rayFunc_)
+      for (std::size_t b = 0; b < numBatches; ++b) rayBatches_[b].resize(std::min(rayStream_.size(), (b + 1) * per) - b * per);
+    // One replica renders the caller's stream in place. Several replicas each get the batches i % R
+    // (src/IpuScene.cpp:676-684) gathered into one contiguous stream, so that every GPU is filled by a single trace.
+    std::vector<std::vector<TraceResult>> perReplica(R > 1 ? R : 0);
+    if (R > 1)
+      for (std::size_t b = 0; b < numBatches; ++b) {
+        const std::size_t lo = b * per, hi = std::min(rayStream_.size(), lo + per);
+        perReplica[b % R].insert(perReplica[b % R].end(), rayStream_.begin() + (long)lo, rayStream_.begin() + (long)hi);
+      }
+    auto streamOf = [&](std::size_t r) -> std::vector<TraceResult>& { return R > 1 ? perReplica[r] : rayStream_; };
 
+    // Phase 1 (untimed, like the reference's compile/load/prepareEngine): device scenes, NIF weights, page-locking.
     std::vector<std::string> errors(R);
+    std::vector<b200rt_scene*> scenes(R, nullptr);
+    std::vector<char> pinned(R, 0);
+    auto forEachReplica = [&](auto&& body) {
+      std::vector<std::thread> threads;
+      for (std::size_t r = 0; r < R; ++r) threads.emplace_back([&, r] { body(r); });
+      for (auto& t : threads) t.join();
+    };
+    forEachReplica([&](std::size_t r) {
+      const b200rt_scene_desc d = makeDesc((int)r);
+      if (b200rt_scene_create(&d, &scenes[r]) != 0) { errors[r] = b200rt_last_error(); return; }
+      if (haveNif_ && data_.pathTrace) {
+        std::vector<b200rt_nif_layer> layers(nif_.layers.size());
+        for (std::size_t i = 0; i < layers.size(); ++i) {
+          layers[i].in_features = nif_.layers[i].in; layers[i].out_features = nif_.layers[i].out;
+          layers[i].kernel_f16 = nif_.layers[i].kernel.data();
+          layers[i].bias_f16 = nif_.layers[i].bias.empty() ? nullptr : nif_.layers[i].bias.data();
+          layers[i].relu = (std::int32_t)nif_.layers[i].relu;
+        }
+        b200rt_nif_desc nd{};
+        nd.embedding_dimension = nif_.embedding; nd.num_layers = (std::uint32_t)layers.size(); nd.layers = layers.data();
+        nd.max = nif_.max; std::copy(nif_.mean, nif_.mean + 3, nd.mean); nd.log_tone_map = (std::int32_t)nif_.logToneMap;
+        if (b200rt_scene_load_nif(scenes[r], &nd) != 0) { errors[r] = b200rt_last_error(); return; }
+        b200rt_scene_set_hdri_rotation(scenes[r], hdriRotationDegrees_);
+        b200rt_scene_set_max_nif_batch_size(scenes[r], nifMaxRaysPerBatch_);
+      }
+      auto& stream = streamOf(r);
+      if (!stream.empty()) pinned[r] = b200rt_host_register(stream.data(), stream.size() * sizeof(TraceResult)) == 0;
+    });
+
+    // Phase 2 (timed; the span of IpuScene::getTraceTimeSecs, src/IpuScene.cpp:672-696): stream in, trace, stream out.
     std::vector<b200rt_trace_stats> stats(R);
     const auto t0 = std::chrono::steady_clock::now();
-    std::vector<std::thread> threads;
-    for (std::size_t r = 0; r < R; ++r) {
-      threads.emplace_back([&, r] {
-        b200rt_scene* sc = nullptr;
-        const b200rt_scene_desc d = makeDesc((int)r);
-        if (b200rt_scene_create(&d, &sc) != 0) { errors[r] = b200rt_last_error(); return; }
-        if (haveNif_ && data_.pathTrace) {
-          std::vector<b200rt_nif_layer> layers(nif_.layers.size());
-          for (std::size_t i = 0; i < layers.size(); ++i) {
-            layers[i].in_features = nif_.layers[i].in; layers[i].out_features = nif_.layers[i].out;
-            layers[i].kernel_f16 = nif_.layers[i].kernel.data();
-            layers[i].bias_f16 = nif_.layers[i].bias.empty() ? nullptr : nif_.layers[i].bias.data();
-            layers[i].relu = (std::int32_t)nif_.layers[i].relu;
-          }
-          b200rt_nif_desc nd{};
-          nd.embedding_dimension = nif_.embedding; nd.num_layers = (std::uint32_t)layers.size(); nd.layers = layers.data();
-          nd.max = nif_.max; std::copy(nif_.mean, nif_.mean + 3, nd.mean); nd.log_tone_map = (std::int32_t)nif_.logToneMap;
-          if (b200rt_scene_load_nif(sc, &nd) != 0) errors[r] = b200rt_last_error();
-          b200rt_scene_set_hdri_rotation(sc, hdriRotationDegrees_);
-          b200rt_scene_set_max_nif_batch_size(sc, nifMaxRaysPerBatch_);
-        }
-        if (errors[r].empty() && !perReplica[r].empty()) {
-          b200rt_trace_params p{};
-          p.rays_per_batch = (std::uint32_t)per;
-          CallbackCtx ctx{this, r, R};
-          if (b200rt_trace(sc, &p, perReplica[r].data(), perReplica[r].size(), rayFunc_ ? &B200Scene::trampoline : nullptr,
-                           &ctx) != 0)
-            errors[r] = b200rt_last_error();
-          b200rt_get_trace_stats(sc, &stats[r]);
-        }
-        b200rt_scene_destroy(sc);
-      });
-    }
-    for (auto& t : threads) t.join();
+    forEachReplica([&](std::size_t r) {
+      auto& stream = streamOf(r);
+      if (!errors[r].empty() || stream.empty()) return;
+      b200rt_trace_params p{};
+      p.rays_per_batch = (std::uint32_t)per;
+      CallbackCtx ctx{this, r, R};
+      if (b200rt_trace(scenes[r], &p, stream.data(), stream.size(), rayFunc_ ? &B200Scene::trampoline : nullptr, &ctx) != 0)
+        errors[r] = b200rt_last_error();
+      b200rt_get_trace_stats(scenes[r], &stats[r]);
+    });
     traceTimeSecs_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    for (std::size_t r = 0; r < R; ++r) {
+      if (pinned[r]) b200rt_host_unregister(streamOf(r).data());
+      if (scenes[r]) b200rt_scene_destroy(scenes[r]);
+    }
     for (auto& e : errors)
       if (!e.empty()) throw std::runtime_error(e);
 
     // un-batch into the caller's stream (src/IpuScene.cpp:715-732)
-    std::vector<std::size_t> cursor(R, 0);
-    for (std::size_t b = 0; b < numBatches; ++b) {
-      const std::size_t r = b % R, n = rayBatches_[b].size();
-      std::copy(perReplica[r].begin() + (long)cursor[r], perReplica[r].begin() + (long)(cursor[r] + n),
-                rayBatches_[b].begin());
-      std::copy(rayBatches_[b].begin(), rayBatches_[b].end(), rayStream_.begin() + (long)(b * per));
-      cursor[r] += n;
+    if (R > 1) {
+      std::vector<std::size_t> cursor(R, 0);
+      for (std::size_t b = 0; b < numBatches; ++b) {
+        const std::size_t r = b % R, n = std::min(rayStream_.size(), (b + 1) * per) - b * per;
+        std::copy(perReplica[r].begin() + (long)cursor[r], perReplica[r].begin() + (long)(cursor[r] + n),
+                  rayStream_.begin() + (long)(b * per));
+        cursor[r] += n;
+      }
     }
     stats_ = b200rt_trace_stats{};
     for (auto& s : stats) {
@@ -240,6 +258,7 @@ class B200Scene {
       stats_.samples += s.samples; stats_.escaped_samples += s.escaped_samples;
       stats_.kernel_launches += s.kernel_launches;
       stats_.kernel_ms = std::max(stats_.kernel_ms, s.kernel_ms);
+      stats_.h2d_ms = std::max(stats_.h2d_ms, s.h2d_ms); stats_.d2h_ms = std::max(stats_.d2h_ms, s.d2h_ms);
     }
   }
 

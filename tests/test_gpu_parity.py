@@ -84,7 +84,7 @@ def test_imported_collada_scenes_bit_exact(B200Scene, port, fixture, normals, re
     with B200Scene(s) as g:
         for trav, res in VARIANTS[:4]:
             got = base.copy()
-            g.execute(got, light_pos=(0.0, 6.0, -3.0), traversal=trav, scene_residency=res)
+            g.execute(got, light_pos=(0.0, 6.0, -3.0), ambient=0.05, traversal=trav, scene_residency=res)
             assert_streams_identical(got, want, f"{fixture} shadow trav={trav} res={res}")
 
 
