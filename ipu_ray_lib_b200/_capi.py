@@ -77,7 +77,7 @@ class TraceParams(C.Structure):
         ("first_sample", C.c_uint32), ("num_samples", C.c_uint32),
         ("rays_per_batch", C.c_uint32), ("traversal", C.c_uint32),
         ("scene_residency", C.c_uint32), ("samples_per_chunk", C.c_uint32),
-        ("count_visits", C.c_uint32), ("reserved", C.c_uint32 * 5),
+        ("count_visits", C.c_uint32), ("primary_pass", C.c_uint32), ("reserved", C.c_uint32 * 4),
     ]
 
 

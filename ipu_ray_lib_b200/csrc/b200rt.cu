@@ -49,6 +49,9 @@ struct DeviceBuffer {
     e = cudaMemset(p, 0, bytes);
     if (e != cudaSuccess) return e;
     if (n && src) e = cudaMemcpy(p, src, n, cudaMemcpyHostToDevice);
+    // A pageable-source cudaMemcpy may return once the data is staged, before the DMA has landed; the kernels that
+    // read this buffer run on the scene's own non-blocking stream, which is not ordered after the default stream.
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
     return e;
   }
   cudaError_t reserve(size_t n) {
@@ -83,7 +86,7 @@ struct b200rt_scene {
   rt::DevScene dev{};
   uint32_t nodeBytes = 0;
   DeviceBuffer nodes, geoms, triVerts, triNormals, spheres, discs, matIDs, materials;
-  DeviceBuffer workCounter, counters;
+  DeviceBuffer workCounter, counters, primA, primB;
   DeviceBuffer rays;                                   // device copy of the stream (host-buffer entry point)
   DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
   DeviceBuffer wfRayO, wfRayD, wfNrm, wfThr, wfCol, wfRng, wfHitA, wfHitB, wfQ0, wfQ1, wfCounts;  // wavefront path state
@@ -96,7 +99,7 @@ struct b200rt_scene {
     cudaSetDevice(device);
     if (nif) rt::nif_destroy(nif);
     for (DeviceBuffer* b : {&nodes, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
-                            &workCounter, &counters, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
+                            &workCounter, &counters, &primA, &primB, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
                             &escapeCount, &wfRayO, &wfRayD, &wfNrm, &wfThr, &wfCol, &wfRng, &wfHitA, &wfHitB, &wfQ0, &wfQ1,
                             &wfCounts})
       b->release();
@@ -175,6 +178,22 @@ cudaError_t dispatch_path_sm(bool count, bool nif, const rt::TraceArgs& a, int g
   return nif ? launch_path_sm<kShared, false, true>(a, g, b, s, st) : launch_path_sm<kShared, false, false>(a, g, b, s, st);
 }
 
+template <bool kShared, bool kOrdered, bool kCount>
+cudaError_t launch_primary(const rt::TraceArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+  auto k = rt::primary_hit_kernel<kShared, kOrdered, kCount>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<grid, block, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <bool kShared, bool kOrdered>
+cudaError_t dispatch_primary(bool count, const rt::TraceArgs& a, int g, int b, size_t s, cudaStream_t st) {
+  return count ? launch_primary<kShared, kOrdered, true>(a, g, b, s, st)
+               : launch_primary<kShared, kOrdered, false>(a, g, b, s, st);
+}
+
 struct LaunchPlan {
   bool shared, ordered, count, stateMachine;
   int grid, block;
@@ -209,6 +228,12 @@ cudaError_t run_shadow(b200rt_scene& sc, const LaunchPlan& L, const rt::TraceArg
                                  : dispatch_shadow<true, false>(L.count, a, L.grid, L.block, L.smem, sc.stream);
   return L.ordered ? dispatch_shadow<false, true>(L.count, a, L.grid, L.block, L.smem, sc.stream)
                    : dispatch_shadow<false, false>(L.count, a, L.grid, L.block, L.smem, sc.stream);
+}
+cudaError_t run_primary(b200rt_scene& sc, const LaunchPlan& L, const rt::TraceArgs& a) {
+  if (L.shared) return L.ordered ? dispatch_primary<true, true>(L.count, a, L.grid, L.block, L.smem, sc.stream)
+                                 : dispatch_primary<true, false>(L.count, a, L.grid, L.block, L.smem, sc.stream);
+  return L.ordered ? dispatch_primary<false, true>(L.count, a, L.grid, L.block, L.smem, sc.stream)
+                   : dispatch_primary<false, false>(L.count, a, L.grid, L.block, L.smem, sc.stream);
 }
 cudaError_t run_path(b200rt_scene& sc, const LaunchPlan& L, bool nif, const rt::TraceArgs& a) {
   if (L.stateMachine)
@@ -300,7 +325,10 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
     const uint32_t first = p.first_sample;
     const uint32_t count = p.num_samples ? p.num_samples : sc.desc.samples_per_pixel;
     const bool wavefront = p.traversal == 4;
-    if (!sc.nif && !wavefront) {
+    static const int envPrimary = [] { const char* e = std::getenv("B200RT_PRIMARY_PASS"); return e ? std::atoi(e) : 0; }();
+    const uint32_t primarySel = p.primary_pass ? p.primary_pass : (uint32_t)envPrimary;  // 0 = auto (on)
+    const bool primaryPass = !wavefront && !L.stateMachine && primarySel != 2;
+    if (!sc.nif && !wavefront && !primaryPass) {
       a.firstSample = first;
       a.endSample = first + count;
       CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
@@ -312,21 +340,31 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
       // Chunks of samples: trace -> (compacted escaped rays) NIF -> ordered accumulate.
       uint32_t chunk = p.samples_per_chunk ? p.samples_per_chunk : 32u;
       // bound the per-path arrays (slots; plus 136 B of path state in wavefront mode) to ~8 / ~20 GiB
-      const size_t perSlot = (3 + 5 + 3 + 1) * sizeof(float) + (wavefront ? 136 : 0);
+      const bool slots = sc.nif || wavefront;  // per-sample colour / escape records handed to NIF + accumulate
+      const bool primB = primaryPass && sc.dev.triNormals != nullptr;
+      const size_t perSlot = (slots ? (3 + 5 + 3 + 1) * sizeof(float) : 0) + (wavefront ? 136 : 0) +
+                             (primaryPass ? (primB ? 32 : 16) : 0);
       const size_t budget = wavefront ? (size_t)20 << 30 : (size_t)8 << 30;
       while (chunk > 1 && (size_t)chunk * n * perSlot > budget) chunk /= 2;
       if (chunk > count) chunk = count ? count : 1;
       if ((size_t)chunk * n > 0xFFFFFFF0ull) return fail(B200RT_ERR_UNSUPPORTED, "ray stream too long for one chunk");
       const size_t P = (size_t)chunk * n;
-      CU_TRY(sc.slotColor.reserve(P * 3 * sizeof(float)));
-      CU_TRY(sc.slotEscape.reserve(P * 5 * sizeof(float)));
-      CU_TRY(sc.slotEnv.reserve(P * 3 * sizeof(float)));
-      CU_TRY(sc.escapeQueue.reserve(P * sizeof(uint32_t)));
       CU_TRY(sc.escapeCount.reserve(16));
-      a.slotColor = (float*)sc.slotColor.p;
-      a.slotEscape = (float*)sc.slotEscape.p;
-      a.escapeQueue = (uint32_t*)sc.escapeQueue.p;
-      a.escapeCount = (uint32_t*)sc.escapeCount.p;
+      if (slots) {
+        CU_TRY(sc.slotColor.reserve(P * 3 * sizeof(float)));
+        CU_TRY(sc.slotEscape.reserve(P * 5 * sizeof(float)));
+        CU_TRY(sc.slotEnv.reserve(P * 3 * sizeof(float)));
+        CU_TRY(sc.escapeQueue.reserve(P * sizeof(uint32_t)));
+        a.slotColor = (float*)sc.slotColor.p;
+        a.slotEscape = (float*)sc.slotEscape.p;
+        a.escapeQueue = (uint32_t*)sc.escapeQueue.p;
+        a.escapeCount = (uint32_t*)sc.escapeCount.p;
+      }
+      if (primaryPass) {
+        CU_TRY(sc.primA.reserve(P * 16));
+        a.primA = (uint4*)sc.primA.p;
+        if (primB) { CU_TRY(sc.primB.reserve(P * 16)); a.primB = (float4*)sc.primB.p; }
+      }
       a.hdriRotation = (sc.hdriRotationDegrees / 360.f) * (float)(2.0 * M_PI);  // src/IpuScene.cpp:641
       rt::WfArgs w{};
       if (wavefront) {
@@ -350,9 +388,10 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
         a.endSample = s0 + c;
         CU_TRY(cudaMemsetAsync(sc.escapeCount.p, 0, 4, sc.stream));
         if (!wavefront) {
-          CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
-          timer.begin(KernelTimer::TRACE, sc.stream);
-          CU_TRY(run_path(sc, L, true, a));
+          CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 8, sc.stream));
+          timer.begin(KernelTimer::TRACE, sc.stream);  // one span: pre-pass + path tracer = the trace step of a chunk
+          if (primaryPass) { CU_TRY(run_primary(sc, L, a)); launches += 1; }
+          CU_TRY(run_path(sc, L, sc.nif != nullptr, a));
           timer.end(sc.stream);
           launches += 1;
         } else {
@@ -399,6 +438,7 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
           if (rc != 0) return fail(B200RT_ERR_CUDA, std::string("NIF evaluation failed: ") + rt::nif_last_error());
           launches += (uint64_t)nifLaunches;
         }
+        if (!slots) continue;  // path tracer without an environment light: rgb was accumulated in the kernel
         const uint32_t threads = 256, blocks = (uint32_t)((n + threads - 1) / threads);
         timer.begin(KernelTimer::ACCUM, sc.stream);
         rt::wf_accumulate_kernel<<<blocks, threads, 0, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,

@@ -201,6 +201,9 @@ NifModel* nif_create(const b200rt_nif_desc& d, int device) {
   m->tcOk = prepare_tc(m, d);
   const char* impl = std::getenv("B200RT_NIF_IMPL");
   if (impl && std::strcmp(impl, "simt") == 0) { m->tcOk = false; m->tcWhyNot = "forced by B200RT_NIF_IMPL=simt"; }
+  // Weight uploads came from pageable memory on the default stream; the kernels run on the caller's non-blocking
+  // stream, so make sure every DMA has landed before the model is handed out.
+  cudaDeviceSynchronize();
   return m;
 }
 

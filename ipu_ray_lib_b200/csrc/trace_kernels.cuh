@@ -47,6 +47,9 @@ struct TraceArgs {
   uint32_t* escapeCount;
   float hdriRotation;       // radians
   int travThreshold;        // state machine: run inner-node steps while at least this many lanes want one
+  // primary-ray pre-pass (null = off): closest hit of every camera ray of the chunk, traced warp-coherently
+  uint4* primA;             // [numRays][chunk] = {t bits, geomID, primID, global triangle index}
+  float4* primB;            // [numRays][chunk] = {b0, b1, b2, -}; only when the scene interpolates normals
 };
 
 __device__ __forceinline__ void flush_counters(DeviceCounters* out, unsigned closest, unsigned occl, const Counters& c,
@@ -149,6 +152,59 @@ __device__ __forceinline__ void escaped_uv(V3 d, float rotation, float& u, float
   v = phi * 0.15915494309189533577f;
 }
 
+// sampleCameraRays (codelets/TraceCodelets.cpp:142-164) with the per-(pixel,sample) stream: seeds `rng`, consumes the
+// two jitter draws and returns the camera-ray direction. Shared by the pre-pass and the path tracer so that both see the
+// same ray bit for bit.
+__device__ __forceinline__ V3 camera_ray(const TraceArgs& a, float row, float col, uint32_t pixelIndex, uint32_t s, Rng& rng) {
+  rng_seed_stream(rng, a.rngKey, pixelIndex, s);
+  const uint64_t ra = rng_next(rng), rb = rng_next(rng);
+  float g0, g1;
+  gaussian_pair(ra, rb, g0, g1);
+  const float pu = row + a.antiAlias * g0;
+  const float pv = col + a.antiAlias * g1;
+  return pixel_to_ray_dir(pv, pu, a.imageWidth, a.imageHeight, a.tanTheta);
+}
+
+// Primary-ray pre-pass. In the path tracer below every lane runs its own path, so a lane's camera ray is traced next to
+// 31 unrelated bounce rays and the warp pays for the longest of them. Camera rays of neighbouring pixels are the one
+// coherent population of the whole render: here a warp traces the same sample of 32 adjacent pixels together (~31 of 32
+// lanes active) and parks the hit; the path tracer then starts each path from the parked hit instead of a traversal.
+// Same ray, same traversal code, same hit -- results do not change, about a third of the path tracer's queries go away.
+template <bool kShared, bool kOrdered, bool kCount>
+__global__ void __launch_bounds__(768) primary_hit_kernel(const TraceArgs a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const uint2* nodes = stage_nodes<kShared>(a, reinterpret_cast<uint2*>(smemRaw));
+  const DevScene& sc = a.scene;
+  const unsigned lane = threadIdx.x & 31;
+  const float inf = __int_as_float(0x7f800000);
+  const uint32_t chunk = a.endSample - a.firstSample;
+  Counters cnt = {0u, 0u};
+  unsigned nClosest = 0;
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.workCounter + 1, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= a.numRays) break;
+    const uint32_t idx = base + lane;
+    if (idx >= a.numRays) continue;
+    const float* tr = a.rays + (size_t)idx * TR_WORDS;
+    const float row = tr[TR_ROW], col = tr[TR_COL];
+    const uint32_t pixelIndex = (uint32_t)row * (uint32_t)a.imageWidth + (uint32_t)col;
+    for (uint32_t s = a.firstSample; s < a.endSample; ++s) {
+      Rng rng;
+      const V3 d = camera_ray(a, row, col, pixelIndex, s, rng);
+      const V3 o = offset_origin(mk(0.f, 0.f, 0.f), d, mk(0.f, 0.f, 1.f));
+      Hit h;
+      nClosest++;
+      closest_hit<kShared, kOrdered, kCount>(sc, nodes, o, d, 0.f, inf, h, cnt);
+      const size_t slot = (size_t)idx * chunk + (s - a.firstSample);
+      a.primA[slot] = make_uint4(__float_as_uint(h.t), h.geomID, h.primID, h.tri);
+      if (a.primB) a.primB[slot] = make_float4(h.b0, h.b1, h.b2, 0.f);
+    }
+  }
+  flush_counters(a.counters, nClosest, 0u, cnt, 0u, 0u);
+}
+
 template <bool kShared, bool kOrdered, bool kCount, bool kNif>
 __global__ void __launch_bounds__(768) path_trace_kernel(const TraceArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -180,35 +236,12 @@ __global__ void __launch_bounds__(768) path_trace_kernel(const TraceArgs a) {
     Rng rng;
     uint32_t s = a.firstSample;
     uint32_t bounce = 0;
-    bool fresh = true;
+    bool live = false;  // the lane holds a ray (o, d, n) that still has to be traced
 
-    while (true) {
-      if (fresh) {
-        if (s == a.endSample) break;
-        // sampleCameraRays (codelets/TraceCodelets.cpp:142-164) with the per-(pixel,sample) stream
-        rng_seed_stream(rng, a.rngKey, pixelIndex, s);
-        const uint64_t ra = rng_next(rng), rb = rng_next(rng);
-        float g0, g1;
-        gaussian_pair(ra, rb, g0, g1);
-        const float pu = row + a.antiAlias * g0;
-        const float pv = col + a.antiAlias * g1;
-        d = pixel_to_ray_dir(pv, pu, a.imageWidth, a.imageHeight, a.tanTheta);
-        o = mk(0.f, 0.f, 0.f);
-        n = mk(0.f, 0.f, 1.f);
-        primID = kInvalidPrim; geomID = kInvalidGeom; flags = 0;
-        thr = mk(1.f, 1.f, 1.f);
-        color = mk(0.f, 0.f, 0.f);
-        bounce = 0;
-        fresh = false;
-        nSamples++;
-      }
-
-      // ---- one iteration of the bounce loop (trace.cpp:125-184) ----
+    // One bounce of the loop in trace.cpp:125-184, from the hit `h` of the ray (o, d) onwards: hit point, emission,
+    // BxDF sample, roulette, path end. Leaves the next ray in (o, d, n) with live = true, or ends the path (s++).
+    auto shade = [&](const Hit& h) {
       bool ended = false, escaped = false;
-      o = offset_origin(o, d, n);
-      Hit h;
-      nClosest++;
-      closest_hit<kShared, kOrdered, kCount>(sc, nodes, o, d, 0.f, inf, h, cnt);
       tMaxOut = h.t;
       if (h.geomID != kInvalidGeom) {
         geomID = h.geomID; primID = h.primID;
@@ -248,7 +281,7 @@ __global__ void __launch_bounds__(768) path_trace_kernel(const TraceArgs a) {
         bounce++;
         if (bounce >= a.maxPathLength) ended = true;
       }
-
+      live = !ended;
       if (ended) {
         if (escaped) nEscaped++;
         if (kNif) {
@@ -275,8 +308,43 @@ __global__ void __launch_bounds__(768) path_trace_kernel(const TraceArgs a) {
           rgb = rgb + color;  // result.rgb += color (trace.cpp:187)
         }
         s++;
-        fresh = true;
       }
+    };
+
+    while (true) {
+      // Regenerate: lanes whose path ended start their next sample(s) until they hold a ray to trace. With the
+      // pre-pass the camera ray's hit is already parked, so its bounce is shaded right here and the lane joins the
+      // traversal below with its first BOUNCE ray -- every trip through the traversal does real work in every lane.
+      while (!live && s != a.endSample) {
+        d = camera_ray(a, row, col, pixelIndex, s, rng);
+        o = mk(0.f, 0.f, 0.f);
+        n = mk(0.f, 0.f, 1.f);
+        primID = kInvalidPrim; geomID = kInvalidGeom; flags = 0;
+        thr = mk(1.f, 1.f, 1.f);
+        color = mk(0.f, 0.f, 0.f);
+        bounce = 0;
+        nSamples++;
+        if (a.primA != nullptr) {
+          o = offset_origin(o, d, n);
+          const size_t slot = (size_t)idx * chunk + (s - a.firstSample);
+          const uint4 pa = a.primA[slot];
+          Hit h;
+          h.t = __uint_as_float(pa.x); h.geomID = pa.y; h.primID = pa.z; h.tri = pa.w; h.node = 0;
+          h.b0 = h.b1 = h.b2 = 0.f;
+          if (a.primB) { const float4 pb = a.primB[slot]; h.b0 = pb.x; h.b1 = pb.y; h.b2 = pb.z; }
+          shade(h);
+        } else {
+          live = true;
+        }
+      }
+      if (!live) break;
+
+      // ---- one iteration of the bounce loop (trace.cpp:125-184) ----
+      o = offset_origin(o, d, n);
+      Hit h;
+      nClosest++;
+      closest_hit<kShared, kOrdered, kCount>(sc, nodes, o, d, 0.f, inf, h, cnt);
+      shade(h);
     }
 
     // write back: rgb running sum + the HitRecord of the last sample (what the reference leaves behind)

@@ -48,14 +48,15 @@ def test_path_trace_bit_exact_all_variants(B200Scene, port, name):
     cw = port.path_trace(s, want)
     with B200Scene(s) as g:
         for trav, res in VARIANTS:
-            got = base.copy()
-            g.execute(got, traversal=trav, scene_residency=res, count_visits=1)
-            assert_streams_identical(got, want, f"{name} path trav={trav} res={res}")
-            st = g.stats()
-            for k in ("closest_hit_queries", "samples", "escaped_samples"):
-                assert st[k] == cw[k], k
-            if trav == 1:
-                assert st["node_visits"] == cw["node_visits"] and st["prim_tests"] == cw["prim_tests"]
+            for pp in ((1, 2) if trav in (1, 2) else (0,)):  # camera rays through the coherent pre-pass, or not
+                got = base.copy()
+                g.execute(got, traversal=trav, scene_residency=res, count_visits=1, primary_pass=pp, samples_per_chunk=4)
+                assert_streams_identical(got, want, f"{name} path trav={trav} res={res} primary_pass={pp}")
+                st = g.stats()
+                for k in ("closest_hit_queries", "samples", "escaped_samples"):
+                    assert st[k] == cw[k], k
+                if trav == 1:
+                    assert st["node_visits"] == cw["node_visits"] and st["prim_tests"] == cw["prim_tests"]
 
 
 @pytest.mark.parametrize("fixture,normals", [("dae_scene", True), ("hdri_scene", False)])
