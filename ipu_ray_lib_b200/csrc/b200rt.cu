@@ -326,8 +326,8 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
     const uint32_t count = p.num_samples ? p.num_samples : sc.desc.samples_per_pixel;
     const bool wavefront = p.traversal == 4;
     static const int envPrimary = [] { const char* e = std::getenv("B200RT_PRIMARY_PASS"); return e ? std::atoi(e) : 0; }();
-    const uint32_t primarySel = p.primary_pass ? p.primary_pass : (uint32_t)envPrimary;  // 0 = auto (on)
-    const bool primaryPass = !wavefront && !L.stateMachine && primarySel != 2;
+    const uint32_t primarySel = p.primary_pass ? p.primary_pass : (uint32_t)envPrimary;  // 0 = auto (off: no measured gain)
+    const bool primaryPass = !wavefront && !L.stateMachine && primarySel == 1;
     if (!sc.nif && !wavefront && !primaryPass) {
       a.firstSample = first;
       a.endSample = first + count;
