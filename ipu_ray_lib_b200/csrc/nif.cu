@@ -64,20 +64,22 @@ struct NifModel {
 
 namespace {
 
-// Builds the B-operand images W[k/8][n][k%8] (fp16, N padded to 16 with zeros) for the tcgen05 kernel. The K order
-// of an image is [rows multiplying the previous activations | bias row + 15 zero rows (the "ones" slice) | rows
-// multiplying the encoded input], matching the A-operand slices the kernel walks. Returns false (with a reason)
-// when the model does not fit the kernel's tiling rules.
+// Builds the B-operand images for the tcgen05 kernel: per layer the four blocks B0..B3 of nif_tc.cuh back to back,
+// each block stored as [k/8][n within its column half][k%8] fp16 (zero padded). K order of the lo blocks:
+// [rows multiplying the previous layer's first 160 outputs | bias row + 15 zero rows (the "ones" slice) | rows
+// multiplying the encoded input]; of the hi blocks: [rows multiplying the remaining outputs]. Returns false (with a
+// reason) when the model does not fit the kernel's tiling rules.
 bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
   auto no = [&](const std::string& why) { m->tcWhyNot = why; return false; };
   const int E = (int)d.embedding_dimension, F = 4 * E;
   if (F % 16 != 0) return no("feature width 4E is not a multiple of 16");
   if (2 + F / 8 > tc::kStaticPlanesMax) return no("encoded input wider than the static region");
+  if ((int)d.num_layers > tc::kMaxLayers) return no("too many layers");
   tc::Params& t = m->tc;
   t = tc::Params{};
   t.numLayers = (int)d.num_layers;
   t.embed = E;
-  int width = F, maxNpad = 16, maxHidden = 16;
+  int width = F, maxHidden = 16, prevN0 = 0;
   std::vector<int> actRows(d.num_layers), featRows(d.num_layers);
   for (uint32_t i = 0; i < d.num_layers; ++i) {
     const b200rt_nif_layer& L = d.layers[i];
@@ -85,8 +87,10 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
     const int K = (int)L.in_features;
     o.N = (int)L.out_features; o.Npad = (o.N + 15) / 16 * 16; o.relu = L.relu;
     const bool last = i + 1 == d.num_layers;
-    if (!last && o.N % 16 != 0) return no("hidden width is not a multiple of 16");
-    if (o.Npad > 512) return no("layer wider than the 512 TMEM columns");
+    if (!last && o.N != tc::kHalfN && o.N != 2 * tc::kHalfN) return no("hidden width is not 160 or 320");
+    if (last && o.Npad > tc::kHalfN) return no("output layer wider than one accumulator slot");
+    o.n0 = std::min(o.Npad, tc::kHalfN);
+    o.n1 = o.Npad - o.n0;
     if (i == 0) {
       if (K != F) return no("first layer does not take the encoded input");
       actRows[i] = 0; featRows[i] = F;
@@ -97,19 +101,19 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
     } else {
       return no("layer input width mismatch");
     }
-    o.actSlices = actRows[i] / 16;
+    o.actLoSlices = std::min(actRows[i], prevN0) / 16;
+    o.actHiSlices = actRows[i] / 16 - o.actLoSlices;
     o.staticSlices = 1 + featRows[i] / 16;
     width = o.N;
-    maxNpad = std::max(maxNpad, o.Npad);
+    prevN0 = o.n0;
     if (!last) maxHidden = std::max(maxHidden, o.N);
   }
   if (width != 3) return no("last layer must have 3 outputs");
   t.actPlanes = maxHidden / 8;
-  t.stageBytes = (tc::kStageK / 8) * maxNpad * 16;
   t.maxv = d.max; t.mean0 = d.mean[0]; t.mean1 = d.mean[1]; t.mean2 = d.mean[2];
   t.logToneMap = d.log_tone_map;
-  m->tcSmem = (size_t)(t.actPlanes + tc::kStaticPlanesMax) * tc::kPlaneBytes + (size_t)tc::kStages * t.stageBytes +
-              (2 * tc::kStages + 2) * 8 + 16;
+  m->tcSmem = (size_t)(t.actPlanes + tc::kStaticPlanesMax) * tc::kPlaneBytes + (size_t)tc::kStages * tc::kStageBytes +
+              (2 * tc::kStages + 4) * 8 + 16;
   int maxSmem = 0;
   cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
   if (m->tcSmem > (size_t)maxSmem) return no("activation tile + weight ring exceed shared memory");
@@ -117,15 +121,30 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
   for (uint32_t i = 0; i < d.num_layers; ++i) {
     const b200rt_nif_layer& L = d.layers[i];
     tc::Layer& o = t.layers[i];
-    const int Keff = 16 * (o.actSlices + o.staticSlices);
-    std::vector<__half> img((size_t)Keff * o.Npad, __float2half(0.f));
     const __half* src = reinterpret_cast<const __half*>(L.kernel_f16);
-    auto put = [&](int k, int n, __half v) { img[((size_t)(k / 8) * o.Npad + n) * 8 + (k % 8)] = v; };
-    for (int n = 0; n < o.N; ++n) {
-      for (int k = 0; k < actRows[i]; ++k) put(k, n, src[(size_t)k * o.N + n]);
-      if (L.bias_f16) put(actRows[i], n, reinterpret_cast<const __half*>(L.bias_f16)[n]);
-      for (int k = 0; k < featRows[i]; ++k) put(actRows[i] + 16 + k, n, src[(size_t)(actRows[i] + k) * o.N + n]);
-    }
+    const __half* bias = reinterpret_cast<const __half*>(L.bias_f16);
+    const int loAct = 16 * o.actLoSlices, hiAct = 16 * o.actHiSlices;
+    const int loK = loAct + 16 * o.staticSlices;
+    std::vector<__half> img;
+    // one block: kRows K-rows x nCols columns starting at column nBase; value(k, n) supplies the entries
+    auto block = [&](int kRows, int nBase, int nCols, auto&& value) {
+      const size_t at = img.size();
+      img.resize(at + (size_t)kRows * nCols, __float2half(0.f));
+      for (int k = 0; k < kRows; ++k)
+        for (int n = 0; n < nCols; ++n)
+          if (nBase + n < o.N) img[at + ((size_t)(k / 8) * nCols + n) * 8 + (k % 8)] = value(k, nBase + n);
+    };
+    auto loValue = [&](int k, int n) -> __half {
+      if (k < loAct) return src[(size_t)k * o.N + n];
+      if (k == loAct) return bias ? bias[n] : __float2half(0.f);
+      if (k < loAct + 16) return __float2half(0.f);
+      return src[(size_t)(actRows[i] + (k - loAct - 16)) * o.N + n];  // encoded-input rows follow the activation rows
+    };
+    auto hiValue = [&](int k, int n) -> __half { return src[(size_t)(loAct + k) * o.N + n]; };
+    block(loK, 0, o.n0, loValue);
+    if (o.n1) block(loK, o.n0, o.n1, loValue);
+    if (hiAct) block(hiAct, 0, o.n0, hiValue);
+    if (hiAct && o.n1) block(hiAct, o.n0, o.n1, hiValue);
     void* dw = nullptr;
     if (cudaMalloc(&dw, img.size() * 2) != cudaSuccess) return no("cudaMalloc failed");
     m->allocs.push_back(dw);
@@ -323,7 +342,7 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
       cudaStreamSynchronize(stream);
       cudaMemcpy(h.data(), dProf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
       cudaFree(dProf);
-      const char* names[] = {"total", "producer wait empty", "mma wait act", "(unused)", "mma phase (issue..commit)",
+      const char* names[] = {"total", "producer wait empty", "mma wait act", "mma wait weights", "mma phase (issue..commit)",
                              "epi wait acc", "epi encode", "epi drain", "tiles"};
       std::fprintf(stderr, "[nif profile] CTA0 of %u, rows %u:", tcGrid, count);
       const double tiles = h[tc::PF_TILES] ? (double)h[tc::PF_TILES] : 1.0;
