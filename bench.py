@@ -409,13 +409,13 @@ def rooflines(prof, peaks, n_local, spp, flops_per_lookup, sm_mhz=None):
          "algorithmic_lane_ops_per_launch": lane_ops / tl, "achieved": lane_ops / trace_s / 1e12,
          "peak": issue_peak / 1e12, "unit": "Tlane-op/s", "frac": lane_ops / trace_s / issue_peak,
          "node_visits_per_query": prof["node_visits_per_query"], "prim_tests_per_query": prof["prim_tests_per_query"],
-         "sm_clock_mhz_for_peak": sm_clock_hz / 1e6, "traffic": traffic.get("path_trace_kernel")},
+         "sm_clock_mhz_for_peak": sm_clock_hz / 1e6, "traffic": (traffic.get("path_trace_kernel") or {}).get("dram_bytes_per_launch"), "traffic_unit": "B per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)"},
         {"kernel": "nif_mlp_kernel", "bound": "tensor", "share_of_step": nif_s / step_s if nif_flops else 0.0,
          "launches_per_step": prof["nif_kernel_launches"], "avg_launch_ms": nif_s * 1e3 / nl,
          "algorithmic_flops_per_launch": nif_flops / nl, "achieved": nif_flops / nif_s / 1e12 if nif_flops else 0.0,
          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
          "frac": nif_flops / nif_s / 1e12 / peaks["bf16_tflops_sustained"] if nif_flops else 0.0,
-         "traffic": traffic.get("nif_mlp_kernel")},
+         "traffic": (traffic.get("nif_mlp_kernel") or {}).get("dram_bytes_per_launch"), "traffic_unit": "B per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)"},
         {"kernel": "TraceResult stream in/out", "bound": "hbm", "algorithmic_bytes_per_step": stream_bytes,
          "achieved": stream_bytes / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
          "frac": stream_bytes / step_s / 1e9 / peaks["hbm_gbs"],
