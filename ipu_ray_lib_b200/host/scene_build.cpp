@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -73,6 +74,8 @@ struct Builder {
   std::vector<BuildPrim>& prims;
   std::vector<BvhNode>& nodes;
   std::uint32_t maxDepth = 0;
+  bool sweep = true;   // B200RT_BVH_SWEEP=0 falls back to the 32-bin estimate everywhere
+  static constexpr std::size_t kSweepLimit = 1u << 16;
 
   static BvhNode pack(const Box& b) {
     BvhNode n;
@@ -88,8 +91,43 @@ struct Builder {
     return n;
   }
 
+  // Exact SAH: every split position along every axis of the centroid-sorted list (O(n log n) per node). Used for
+  // ranges up to kSweepLimit primitives; larger ranges use the binned estimate below.
+  std::size_t splitSweep(std::size_t b, std::size_t e) {
+    const std::size_t n = e - b;
+    float bestCost = INFINITY;
+    int bestAxis = -1;
+    std::size_t bestLeft = 0;
+    std::vector<std::uint32_t> order(n), bestOrder;
+    std::vector<float> rightArea(n + 1);
+    for (int axis = 0; axis < 3; ++axis) {
+      for (std::size_t i = 0; i < n; ++i) order[i] = (std::uint32_t)i;
+      std::stable_sort(order.begin(), order.end(), [&](std::uint32_t x, std::uint32_t y) {
+        return prims[b + x].centroid[axis] < prims[b + y].centroid[axis];
+      });
+      Box acc;
+      for (std::size_t i = n; i-- > 1;) {
+        acc.grow(prims[b + order[i]].box);
+        rightArea[i] = acc.halfArea();
+      }
+      acc = Box();
+      for (std::size_t i = 1; i < n; ++i) {  // left = first i primitives
+        acc.grow(prims[b + order[i - 1]].box);
+        const float cost = acc.halfArea() * (float)i + rightArea[i] * (float)(n - i);
+        if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestLeft = i; }
+      }
+      if (bestAxis == axis) bestOrder = order;
+    }
+    if (bestAxis < 0) return b + n / 2;
+    std::vector<BuildPrim> tmp(n);
+    for (std::size_t i = 0; i < n; ++i) tmp[i] = prims[b + bestOrder[i]];
+    std::copy(tmp.begin(), tmp.end(), prims.begin() + (long)b);
+    return b + bestLeft;
+  }
+
   // Returns the split position in [b+1, e-1]; partitions prims[b,e) in place.
   std::size_t split(std::size_t b, std::size_t e) {
+    if (sweep && e - b <= kSweepLimit) return splitSweep(b, e);
     Box cb;
     for (std::size_t i = b; i < e; ++i) cb.grow(prims[i].centroid, prims[i].centroid);
     float bestCost = INFINITY;
@@ -182,6 +220,7 @@ std::uint32_t buildCompactBvh(const float* primBounds, const std::uint32_t* ids,
   nodes.clear();
   nodes.reserve(2 * (std::size_t)n - 1);
   Builder builder{prims, nodes};
+  if (const char* e = std::getenv("B200RT_BVH_SWEEP")) builder.sweep = e[0] != '0';
   std::uint32_t root;
   builder.build(0, n, 1, root);
   return builder.maxDepth;
