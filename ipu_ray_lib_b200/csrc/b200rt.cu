@@ -89,7 +89,7 @@ struct b200rt_scene {
   DeviceBuffer workCounter, counters, primA, primB;
   DeviceBuffer rays;                                   // device copy of the stream (host-buffer entry point)
   DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
-  DeviceBuffer wfRayO, wfRayD, wfNrm, wfThr, wfCol, wfRng, wfHitA, wfHitB, wfQ0, wfQ1, wfCounts;  // wavefront path state
+  DeviceBuffer wfRayO, wfRayD, wfNrm, wfThr, wfRng, wfHitA, wfHitB, wfQ0, wfQ1, wfCounts;  // wavefront path state
   b200rt_trace_stats stats{};
   float hdriRotationDegrees = 0.f;
   size_t maxNifBatch = 0;
@@ -100,7 +100,7 @@ struct b200rt_scene {
     if (nif) rt::nif_destroy(nif);
     for (DeviceBuffer* b : {&nodes, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
                             &workCounter, &counters, &primA, &primB, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
-                            &escapeCount, &wfRayO, &wfRayD, &wfNrm, &wfThr, &wfCol, &wfRng, &wfHitA, &wfHitB, &wfQ0, &wfQ1,
+                            &escapeCount, &wfRayO, &wfRayD, &wfNrm, &wfThr, &wfRng, &wfHitA, &wfHitB, &wfQ0, &wfQ1,
                             &wfCounts})
       b->release();
     if (evStart) cudaEventDestroy(evStart);
@@ -342,7 +342,7 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
       // bound the per-path arrays (slots; plus 136 B of path state in wavefront mode) to ~8 / ~20 GiB
       const bool slots = sc.nif || wavefront;  // per-sample colour / escape records handed to NIF + accumulate
       const bool primB = primaryPass && sc.dev.triNormals != nullptr;
-      const size_t perSlot = (slots ? (3 + 5 + 3 + 1) * sizeof(float) : 0) + (wavefront ? 136 : 0) +
+      const size_t perSlot = (slots ? (3 + 5 + 3 + 1) * sizeof(float) : 0) + (wavefront ? 120 : 0) +
                              (primaryPass ? (primB ? 32 : 16) : 0);
       const size_t budget = wavefront ? (size_t)20 << 30 : (size_t)8 << 30;
       while (chunk > 1 && (size_t)chunk * n * perSlot > budget) chunk /= 2;
@@ -368,18 +368,21 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
       a.hdriRotation = (sc.hdriRotationDegrees / 360.f) * (float)(2.0 * M_PI);  // src/IpuScene.cpp:641
       rt::WfArgs w{};
       if (wavefront) {
-        for (DeviceBuffer* b : {&sc.wfRayO, &sc.wfRayD, &sc.wfNrm, &sc.wfThr, &sc.wfCol, &sc.wfRng, &sc.wfHitA, &sc.wfHitB})
+        if (sc.desc.max_path_length > 255) return fail(B200RT_ERR_UNSUPPORTED, "wavefront path tracer: max_path_length > 255");
+        for (DeviceBuffer* b : {&sc.wfRayO, &sc.wfRayD, &sc.wfNrm, &sc.wfThr, &sc.wfRng, &sc.wfHitA})
           CU_TRY(b->reserve(P * 16));
+        const bool needBary = sc.dev.triNormals != nullptr;  // barycentrics only feed interpolated normals
+        if (needBary) CU_TRY(sc.wfHitB.reserve(P * 16));
         CU_TRY(sc.wfQ0.reserve(P * 4));
         CU_TRY(sc.wfQ1.reserve(P * 4));
         CU_TRY(sc.wfCounts.reserve(16));
         w.b.rayO = (float4*)sc.wfRayO.p; w.b.rayD = (float4*)sc.wfRayD.p; w.b.nrm = (float4*)sc.wfNrm.p;
-        w.b.thr = (float4*)sc.wfThr.p; w.b.col = (float4*)sc.wfCol.p; w.b.rng = (uint4*)sc.wfRng.p;
-        w.b.hitA = (float4*)sc.wfHitA.p; w.b.hitB = (float4*)sc.wfHitB.p;
+        w.b.thr = (float4*)sc.wfThr.p; w.b.rng = (uint4*)sc.wfRng.p;
+        w.b.hitA = (float4*)sc.wfHitA.p; w.b.hitB = needBary ? (float4*)sc.wfHitB.p : nullptr;
         w.b.queue[0] = (uint32_t*)sc.wfQ0.p; w.b.queue[1] = (uint32_t*)sc.wfQ1.p;
         w.b.counts = (uint32_t*)sc.wfCounts.p;
         w.lastSample = first + count - 1;
-        static const int envWf = [] { const char* e = std::getenv("B200RT_WF_THRESHOLD"); return e ? std::atoi(e) : 20; }();
+        static const int envWf = [] { const char* e = std::getenv("B200RT_WF_THRESHOLD"); return e ? std::atoi(e) : 8; }();
         w.travThreshold = envWf;
       }
       for (uint32_t s0 = first; s0 < first + count; s0 += chunk) {

@@ -21,15 +21,18 @@
 
 namespace rt {
 
+// Per-path record, kept as small as the arithmetic allows because wf_shade is bound by it (HBM): 64 B carried from
+// bounce to bounce + a 16 B hit (32 B when the scene interpolates normals). The running colour lives in slotColor (the
+// array the accumulate kernel reads anyway) and is only touched on emissive hits; the normal is carried only for paths
+// of the call's last sample, whose HitRecord is what the reference leaves in the ray stream.
 struct WfBuffers {
-  float4* rayO;       // [P] origin.xyz (offset applied), w = tMax of the last intersect (HitRecord::r.tMax)
-  float4* rayD;       // [P] direction.xyz
-  float4* nrm;        // [P] normal.xyz, w = primID bits
-  float4* thr;        // [P] throughput.xyz, w = (geomID | flags << 16) bits
-  float4* col;        // [P] colour.xyz, w = bounce bits
+  float4* rayO;       // [P] origin.xyz (offset applied), w = bounce | flags << 8 | geomID << 16
+  float4* rayD;       // [P] direction.xyz, w = primID bits
+  float4* thr;        // [P] throughput.xyz, w = tMax of the last intersect (HitRecord::r.tMax)
   uint4* rng;         // [P] xoroshiro state {s0.lo, s0.hi, s1.lo, s1.hi}
+  float4* nrm;        // [P] normal.xyz; read and written only for paths of the last sample
   float4* hitA;       // [P] t, geomID bits, primID bits, tri bits
-  float4* hitB;       // [P] b0, b1, b2
+  float4* hitB;       // [P] b0, b1, b2; only when the scene interpolates normals (else null)
   uint32_t* queue[2];  // [P] path ids of the current / next bounce
   uint32_t* counts;   // [0],[1] queue sizes, [2] fetch cursor of wf_trace
 };
@@ -65,12 +68,13 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(const WfArgs a) {
     const V3 d = pixel_to_ray_dir(pv, pu, t.imageWidth, t.imageHeight, t.tanTheta);
     const V3 n = mk(0.f, 0.f, 1.f);
     const V3 o = offset_origin(mk(0.f, 0.f, 0.f), d, n);  // first offsetRay of the bounce loop (trace.cpp:126)
-    a.b.rayO[p] = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
-    a.b.rayD[p] = make_float4(d.x, d.y, d.z, 0.f);
-    a.b.nrm[p] = make_float4(n.x, n.y, n.z, __uint_as_float(kInvalidPrim));
-    a.b.thr[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(kInvalidGeom));
-    a.b.col[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+    a.b.rayO[p] = make_float4(o.x, o.y, o.z, __uint_as_float(kInvalidGeom << 16));  // bounce 0, no flags
+    a.b.rayD[p] = make_float4(d.x, d.y, d.z, __uint_as_float(kInvalidPrim));
+    a.b.thr[p] = make_float4(1.f, 1.f, 1.f, __int_as_float(0x7f800000));
     a.b.rng[p] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
+    if (s == a.lastSample) a.b.nrm[p] = make_float4(n.x, n.y, n.z, 0.f);
+    float* sc3 = t.slotColor + 3 * (size_t)p;
+    sc3[0] = 0.f; sc3[1] = 0.f; sc3[2] = 0.f;
     a.b.queue[0][p] = p;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[0] = a.numPaths;
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(768) wf_trace_kernel(const WfArgs a) {
       if (phase == WF_FETCH) {
         if (path != 0xFFFFFFFFu) {
           a.b.hitA[path] = make_float4(hit.t, __uint_as_float(hit.geomID), __uint_as_float(hit.primID), __uint_as_float(hit.tri));
-          a.b.hitB[path] = make_float4(hit.b0, hit.b1, hit.b2, 0.f);
+          if (a.b.hitB) a.b.hitB[path] = make_float4(hit.b0, hit.b1, hit.b2, 0.f);
         }
         const uint32_t qi = claimBase + (uint32_t)__popc(mF & ((1u << lane) - 1u));
         if (qi >= count) {
@@ -231,17 +235,24 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
     uint32_t appendSlot = 0xFFFFFFFFu, p = 0;
     if (valid) {
       p = queueIn[i];
-      const float4 ha = a.b.hitA[p], hb = a.b.hitB[p];
-      const float4 ro = a.b.rayO[p], rd = a.b.rayD[p], nn = a.b.nrm[p], th = a.b.thr[p], cl = a.b.col[p];
+      const float4 ha = a.b.hitA[p];
+      const float4 ro = a.b.rayO[p], rd = a.b.rayD[p], th = a.b.thr[p];
       const uint4 rs = a.b.rng[p];
       Hit hit;
       hit.t = ha.x; hit.geomID = __float_as_uint(ha.y); hit.primID = __float_as_uint(ha.z); hit.tri = __float_as_uint(ha.w);
-      hit.node = 0; hit.b0 = hb.x; hit.b1 = hb.y; hit.b2 = hb.z;
-      V3 o = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z), n = mk(nn.x, nn.y, nn.z);
-      V3 thr = mk(th.x, th.y, th.z), color = mk(cl.x, cl.y, cl.z);
-      uint32_t primID = __float_as_uint(nn.w);
-      uint32_t geomID = __float_as_uint(th.w) & 0xffffu, flags = __float_as_uint(th.w) >> 16;
-      uint32_t bounce = __float_as_uint(cl.w);
+      hit.node = 0; hit.b0 = hit.b1 = hit.b2 = 0.f;
+      if (a.b.hitB) { const float4 hb = a.b.hitB[p]; hit.b0 = hb.x; hit.b1 = hb.y; hit.b2 = hb.z; }
+      const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
+      const uint32_t s = t.firstSample + c;
+      const bool lastOne = s == a.lastSample;  // this path's HitRecord is the one left in the ray stream
+      V3 o = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z), n = mk(0.f, 0.f, 1.f);
+      if (lastOne) { const float4 nn = a.b.nrm[p]; n = mk(nn.x, nn.y, nn.z); }
+      V3 thr = mk(th.x, th.y, th.z);
+      V3 emitted = mk(0.f, 0.f, 0.f);  // thr * emission picked up at this bounce
+      bool gotEmission = false, poisoned = false;
+      const uint32_t packed = __float_as_uint(ro.w);
+      uint32_t bounce = packed & 0xffu, flags = (packed >> 8) & 0xffu, geomID = packed >> 16;
+      uint32_t primID = __float_as_uint(rd.w);
       Rng rng;
       rng.s0 = (uint64_t)rs.x | ((uint64_t)rs.y << 32);
       rng.s1 = (uint64_t)rs.z | ((uint64_t)rs.w << 32);
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
         o = o + d * hit.t;
         n = hit_normal(sc, hit, o);
         const Mat m = load_material(sc, geomID);
-        if (m.emissive) color = color + thr * m.emission;
+        if (m.emissive) { emitted = thr * m.emission; gotEmission = true; }
         if (m.type == 0) {
           const float u1 = rng_uniform(rng);
           const float u2 = rng_uniform(rng);
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
           d = dielectric_dir(d, n, m.ior, u1, refracted);
           if (refracted) thr = thr * m.albedo;
         } else {
-          color = color * __int_as_float(0x7fc00000);  // poisons rgb like result.rgb *= NaN (trace.cpp:167)
+          poisoned = true;  // poisons rgb like result.rgb *= NaN (trace.cpp:167)
           flags |= kFlagError;
         }
       } else {
@@ -289,21 +300,24 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
         if (bounce >= t.maxPathLength) ended = true;
       }
 
-      const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
-      const uint32_t s = t.firstSample + c;
+      // running colour of the path: color = color + thr * emission, then (unknown material) color = color * NaN
+      if (gotEmission || poisoned) {
+        float* sc3 = t.slotColor + 3 * (size_t)p;
+        V3 color = mk(sc3[0], sc3[1], sc3[2]);
+        if (gotEmission) color = color + emitted;
+        if (poisoned) color = color * __int_as_float(0x7fc00000);
+        sc3[0] = color.x; sc3[1] = color.y; sc3[2] = color.z;
+      }
       if (!ended) {
         const V3 on = offset_origin(o, d, n);  // offsetRay at the top of the next iteration (trace.cpp:126)
-        a.b.rayO[p] = make_float4(on.x, on.y, on.z, tMaxOut);
-        a.b.rayD[p] = make_float4(d.x, d.y, d.z, 0.f);
-        a.b.nrm[p] = make_float4(n.x, n.y, n.z, __uint_as_float(primID));
-        a.b.thr[p] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(geomID | (flags << 16)));
-        a.b.col[p] = make_float4(color.x, color.y, color.z, __uint_as_float(bounce));
+        a.b.rayO[p] = make_float4(on.x, on.y, on.z, __uint_as_float(bounce | (flags << 8) | (geomID << 16)));
+        a.b.rayD[p] = make_float4(d.x, d.y, d.z, __uint_as_float(primID));
+        a.b.thr[p] = make_float4(thr.x, thr.y, thr.z, tMaxOut);
         a.b.rng[p] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
+        if (lastOne) a.b.nrm[p] = make_float4(n.x, n.y, n.z, 0.f);
         survive = true;
       } else {
         if (escaped) nEscaped++;
-        float* sc3 = t.slotColor + 3 * (size_t)p;
-        sc3[0] = color.x; sc3[1] = color.y; sc3[2] = color.z;
         if (kNif) {
           float* se = t.slotEscape + 5 * (size_t)p;
           float u = -1.f, v = 0.f;
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
           se[0] = thr.x; se[1] = thr.y; se[2] = thr.z; se[3] = u; se[4] = v;
           if (escaped) appendSlot = p;
         }
-        if (s == a.lastSample) {
+        if (lastOne) {
           // the HitRecord the reference leaves in the stream is the last sample's
           float* tr = t.rays + (size_t)idx * TR_WORDS;
           tr[TR_ORIGIN] = o.x; tr[TR_ORIGIN + 1] = o.y; tr[TR_ORIGIN + 2] = o.z;
