@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(768) wf_trace_kernel(const WfArgs a) {
   uint2 stack[kMaxStack];
   int sp = 0;
   int phase = WF_FETCH;
+  // ray ids are claimed from the bounce's queue kClaim at a time per warp: one same-address atomic per 128 rays
+  // instead of one per fetch step (a fetch step serves ~4 lanes)
+  constexpr uint32_t kClaim = 128;
+  uint32_t wNext = 0, wEnd = 0;  // warp-uniform: the unclaimed part of this warp's current batch
 
   auto pop_next = [&]() {
     bool found = false;
@@ -170,19 +174,24 @@ __global__ void __launch_bounds__(768) wf_trace_kernel(const WfArgs a) {
         pop_next();
       }
     } else {
-      // lanes that finished a query store its result and claim the next ray id together
-      uint32_t claimBase = 0;
-      {
-        const int leader = __ffs(mF) - 1;
-        if ((int)lane == leader) claimBase = atomicAdd(cursor, (uint32_t)cF);
-        claimBase = __shfl_sync(full, claimBase, leader);
+      // lanes that finished a query store its result and take the next ray ids of the warp's batch
+      if (wNext == wEnd) {
+        uint32_t claimBase = 0;
+        if (lane == 0) claimBase = atomicAdd(cursor, kClaim);
+        wNext = __shfl_sync(full, claimBase, 0);
+        wEnd = wNext + kClaim;
       }
-      if (phase == WF_FETCH) {
+      const uint32_t avail = wEnd - wNext;
+      const uint32_t rank = (uint32_t)__popc(mF & ((1u << lane) - 1u));
+      const bool served = phase == WF_FETCH && rank < avail;  // the others retry on the next fetch step
+      const uint32_t qi = wNext + rank;
+      wNext += min((uint32_t)cF, avail);
+      if (served) {
         if (path != 0xFFFFFFFFu) {
           a.b.hitA[path] = make_float4(hit.t, __uint_as_float(hit.geomID), __uint_as_float(hit.primID), __uint_as_float(hit.tri));
           if (a.b.hitB) a.b.hitB[path] = make_float4(hit.b0, hit.b1, hit.b2, 0.f);
+          path = 0xFFFFFFFFu;
         }
-        const uint32_t qi = claimBase + (uint32_t)__popc(mF & ((1u << lane) - 1u));
         if (qi >= count) {
           path = 0xFFFFFFFFu;
           phase = WF_DONE;
@@ -225,7 +234,9 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
   const uint32_t count = a.b.counts[a.qIn];
   uint32_t* countOut = a.b.counts + (a.qIn ^ 1);
   unsigned nSamples = 0, nEscaped = 0;
-  // whole warps iterate together so the ballots below see converged lanes
+  __shared__ uint32_t sCount[2][8];
+  static_assert(256 / 32 == 8, "block-level append assumes 8 warps");
+  // whole blocks iterate together (uniform trip count) so the ballots and barriers below see converged threads
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t rounds = (count + stride - 1) / stride;
   for (uint32_t r = 0; r < rounds; ++r) {
@@ -339,26 +350,34 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
         }
       }
     }
-    // regroup: survivors go to the other queue, escaped slots to the NIF queue (warp-aggregated appends)
+    // regroup: survivors go to the other queue, escaped slots to the NIF queue. Appends are aggregated over the whole
+    // block (one same-address atomic per 256 paths and queue): every warp posts its two counts, warp 0 reserves both
+    // ranges, each warp then knows its offset.
     {
-      const unsigned m = __ballot_sync(full, survive);
-      if (m) {
-        const int leader = __ffs(m) - 1;
+      const unsigned mS = __ballot_sync(full, survive);
+      const unsigned mE = kNif ? __ballot_sync(full, appendSlot != 0xFFFFFFFFu) : 0u;
+      const int warp = threadIdx.x >> 5;
+      if (lane == 0) { sCount[0][warp] = (uint32_t)__popc(mS); sCount[1][warp] = (uint32_t)__popc(mE); }
+      __syncthreads();
+      if (warp == 0) {
+        // exclusive scan of the 8 warp counts of each queue in lanes 0..7 / 8..15
+        const int q = lane >> 3, w = lane & 7;
+        uint32_t v = lane < 16 ? sCount[q][w] : 0u, incl = v;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+          const uint32_t up = __shfl_up_sync(full, incl, off, 8);
+          if (w >= off) incl += up;
+        }
         uint32_t base = 0;
-        if ((int)lane == leader) base = atomicAdd(countOut, (uint32_t)__popc(m));
-        base = __shfl_sync(full, base, leader);
-        if (survive) queueOut[base + __popc(m & ((1u << lane) - 1u))] = p;
+        if (lane == 7 && incl) base = atomicAdd(countOut, incl);
+        if (lane == 15 && incl) base = atomicAdd(t.escapeCount, incl);
+        base = __shfl_sync(full, base, (lane & 8) | 7, 32);
+        if (lane < 16) sCount[q][w] = base + incl - v;
       }
-    }
-    if (kNif) {
-      const unsigned m = __ballot_sync(full, appendSlot != 0xFFFFFFFFu);
-      if (m) {
-        const int leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if ((int)lane == leader) base = atomicAdd(t.escapeCount, (uint32_t)__popc(m));
-        base = __shfl_sync(full, base, leader);
-        if (appendSlot != 0xFFFFFFFFu) t.escapeQueue[base + __popc(m & ((1u << lane) - 1u))] = appendSlot;
-      }
+      __syncthreads();
+      if (survive) queueOut[sCount[0][warp] + __popc(mS & ((1u << lane) - 1u))] = p;
+      if (kNif && appendSlot != 0xFFFFFFFFu) t.escapeQueue[sCount[1][warp] + __popc(mE & ((1u << lane) - 1u))] = appendSlot;
+      __syncthreads();  // sCount is rewritten in the next round
     }
   }
   flush_counters(t.counters, 0u, 0u, Counters{0u, 0u}, nSamples, nEscaped);
