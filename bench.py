@@ -368,8 +368,8 @@ def kernel_breakdown(g, work, pristine, n_local, stream, params, nif):
     work.copy_(pristine)
     g.execute_device(work.data_ptr(), n_local, stream=stream, **params)
     st = g.stats()
-    for k in ("kernel_ms", "trace_kernel_ms", "nif_kernel_ms", "accumulate_kernel_ms", "kernel_launches",
-              "trace_kernel_launches", "nif_kernel_launches", "escaped_samples", "samples"):
+    for k in ("kernel_ms", "trace_kernel_ms", "nif_kernel_ms", "accumulate_kernel_ms", "shade_kernel_ms", "kernel_launches",
+              "trace_kernel_launches", "nif_kernel_launches", "shade_kernel_launches", "escaped_samples", "samples"):
         out[k] = st[k]
     out["queries"] = st["closest_hit_queries"] + st["occlusion_queries"]
     # work counters (node visits / primitive tests) from a reduced-spp instrumented run, scaled per query
@@ -403,24 +403,42 @@ def rooflines(prof, peaks, n_local, spp, flops_per_lookup, sm_mhz=None):
     nif_flops = float(prof["escaped_samples"]) * flops_per_lookup
     nl = max(prof["nif_kernel_launches"], 1)
     tl = max(prof["trace_kernel_launches"], 1)
+    wavefront = prof.get("shade_kernel_launches", 0) > 0
+    trace_name = "wf_trace_kernel" if wavefront else "path_trace_kernel"
+    tr = traffic.get(trace_name) or {}
+    unit_note = "B per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)"
     kernels = [
-        {"kernel": "path_trace_kernel", "bound": "issue", "share_of_step": trace_s / step_s,
+        {"kernel": trace_name, "bound": "issue", "share_of_step": trace_s / step_s,
          "launches_per_step": prof["trace_kernel_launches"], "avg_launch_ms": trace_s * 1e3 / tl,
          "algorithmic_lane_ops_per_launch": lane_ops / tl, "achieved": lane_ops / trace_s / 1e12,
          "peak": issue_peak / 1e12, "unit": "Tlane-op/s", "frac": lane_ops / trace_s / issue_peak,
          "node_visits_per_query": prof["node_visits_per_query"], "prim_tests_per_query": prof["prim_tests_per_query"],
-         "sm_clock_mhz_for_peak": sm_clock_hz / 1e6, "traffic": (traffic.get("path_trace_kernel") or {}).get("dram_bytes_per_launch"), "traffic_unit": "B per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)"},
+         "sm_clock_mhz_for_peak": sm_clock_hz / 1e6, "traffic": tr.get("dram_bytes_per_launch"), "traffic_unit": unit_note,
+         "note": ("one launch per bounce and chunk; launches of late bounces are nearly empty" if wavefront else
+                  "one launch per chunk: camera ray, traversal and shading of every bounce")},
         {"kernel": "nif_mlp_kernel", "bound": "tensor", "share_of_step": nif_s / step_s if nif_flops else 0.0,
          "launches_per_step": prof["nif_kernel_launches"], "avg_launch_ms": nif_s * 1e3 / nl,
          "algorithmic_flops_per_launch": nif_flops / nl, "achieved": nif_flops / nif_s / 1e12 if nif_flops else 0.0,
          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
          "frac": nif_flops / nif_s / 1e12 / peaks["bf16_tflops_sustained"] if nif_flops else 0.0,
-         "traffic": (traffic.get("nif_mlp_kernel") or {}).get("dram_bytes_per_launch"), "traffic_unit": "B per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)"},
+         "traffic": (traffic.get("nif_mlp_kernel") or {}).get("dram_bytes_per_launch"), "traffic_unit": unit_note},
+    ]
+    if wavefront:
+        # wf_generate + wf_shade: HBM-bound on the path record. Algorithmic bytes per path-bounce: 84 B read (queue id,
+        # hit, origin, direction, throughput, RNG) + 68 B written for the ~70 % that survive; 80 B per path at generate.
+        shade_s = max(prof["shade_kernel_ms"] * 1e-3, 1e-9)
+        shade_bytes = prof["queries"] * (84.0 + 0.7 * 68.0) + prof["samples"] * 80.0
+        sl = max(prof["shade_kernel_launches"], 1)
+        kernels.append({"kernel": "wf_shade_kernel (+ wf_generate)", "bound": "hbm", "share_of_step": shade_s / step_s,
+                        "launches_per_step": prof["shade_kernel_launches"], "avg_launch_ms": shade_s * 1e3 / sl,
+                        "algorithmic_bytes_per_launch": shade_bytes / sl, "achieved": shade_bytes / shade_s / 1e9,
+                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": shade_bytes / shade_s / 1e9 / peaks["hbm_gbs"],
+                        "traffic": (traffic.get("wf_shade_kernel") or {}).get("dram_bytes_per_launch"), "traffic_unit": unit_note})
+    kernels.append(
         {"kernel": "TraceResult stream in/out", "bound": "hbm", "algorithmic_bytes_per_step": stream_bytes,
          "achieved": stream_bytes / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
          "frac": stream_bytes / step_s / 1e9 / peaks["hbm_gbs"],
-         "note": "168 B/ray/render amortised over all spp: HBM is idle by design in a multi-sample render"},
-    ]
+         "note": "168 B/ray/render amortised over all spp: HBM is idle by design in a multi-sample render"})
     dominant = kernels[0] if trace_s >= nif_s or not nif_flops else kernels[1]
     roof = {"kernel": dominant["kernel"], "bound": dominant["bound"], "achieved": dominant["achieved"],
             "peak": dominant["peak"], "unit": dominant["unit"], "frac": dominant["frac"],

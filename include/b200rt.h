@@ -84,13 +84,14 @@ typedef struct b200rt_trace_params {
   uint32_t first_sample;       /* path-trace: first sample index (for resuming); default 0 */
   uint32_t num_samples;        /* path-trace: samples to take; 0 = scene.samples_per_pixel */
   uint32_t rays_per_batch;     /* callback granularity; 0 = 8640 * rays_per_worker default (src/IpuScene.cpp:78-108) */
-  uint32_t traversal;          /* 0 = auto (renders: 2; bare queries: 1), 1 = reference-order DFS (identical visiting
+  uint32_t traversal;          /* 0 = auto (path-trace renders: 4; shadow-trace renders: 2; bare queries: 1), 1 = reference-order DFS (identical visiting
                                 * order, identical answers for ANY ray), 2 = near-first ordered DFS (same answers for
                                 * unit-length directions, which is all a render produces; ties go to the lowest leaf
                                 * index like the reference's pre-order walk), 3 = near-first DFS with the path tracer
                                 * run as a warp-scheduled state machine (same arithmetic as 2; measured slower, kept selectable),
-                                * 4 = wavefront path tracer: per-bounce generate / trace / shade kernels over path queues in
-                                * HBM (same arithmetic and results as 2; measured on par, kept selectable) */
+                                * 4 = wavefront path tracer: per-bounce trace / shade kernels over path queues in HBM with
+                                * near-first traversal (same arithmetic and results as 2; 38 ms vs 54 ms per 32-spp chunk
+                                * of the bench workload) */
   uint32_t scene_residency;    /* 0 = auto, 1 = BVH staged in shared memory, 2 = global/L2-resident */
   uint32_t samples_per_chunk;  /* path-trace+NIF: samples per wavefront chunk; 0 = auto */
   uint32_t count_visits;       /* 1 = also count node visits / primitive tests (slower; parity tests) */
@@ -114,11 +115,12 @@ typedef struct b200rt_trace_stats {
   double   h2d_ms, d2h_ms;        /* host<->device copies of the ray stream (host-buffer entry points only) */
   double   trace_secs;            /* wall time; same span as IpuScene::getTraceTimeSecs (src/IpuScene.cpp:672-696) */
   uint64_t kernel_launches;       /* number of kernels this library launched */
-  double   trace_kernel_ms;       /* sum over launches of shadow_trace / path_trace kernel time (CUDA events) */
+  double   trace_kernel_ms;       /* sum over launches of shadow_trace / path_trace / wf_trace kernel time (CUDA events) */
   double   nif_kernel_ms;         /* sum over launches of the NIF MLP kernel time */
   double   accumulate_kernel_ms;  /* sum over launches of the ordered rgb accumulation kernel */
   uint64_t trace_kernel_launches, nif_kernel_launches;
-  uint64_t reserved[2];
+  double   shade_kernel_ms;       /* wavefront path tracer: sum over launches of the generate + shade kernels */
+  uint64_t shade_kernel_launches;
 } b200rt_trace_stats;
 
 /* Called once per finished ray batch with (batch_index, rays, n, user).

@@ -90,7 +90,7 @@ class TraceStats(C.Structure):
         ("trace_secs", C.c_double), ("kernel_launches", C.c_uint64),
         ("trace_kernel_ms", C.c_double), ("nif_kernel_ms", C.c_double), ("accumulate_kernel_ms", C.c_double),
         ("trace_kernel_launches", C.c_uint64), ("nif_kernel_launches", C.c_uint64),
-        ("reserved", C.c_uint64 * 2),
+        ("shade_kernel_ms", C.c_double), ("shade_kernel_launches", C.c_uint64),
     ]
 
 

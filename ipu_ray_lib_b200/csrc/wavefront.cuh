@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(const WfArgs a) {
 enum : int { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2, WF_DONE = 3 };
 
 template <bool kShared, bool kCount>
-__global__ void __launch_bounds__(768) wf_trace_kernel(const WfArgs a) {
+__global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const uint2* nodes = stage_nodes<kShared>(a.t, reinterpret_cast<uint2*>(smemRaw));
   const DevScene& sc = a.t.scene;
