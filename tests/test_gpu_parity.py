@@ -89,6 +89,26 @@ def test_imported_collada_scenes_bit_exact(B200Scene, port, fixture, normals, re
             assert_streams_identical(got, want, f"{fixture} shadow trav={trav} res={res}")
 
 
+@pytest.mark.parametrize("max_len,roulette,spp,chunk", [(1, 3, 4, 0), (2, 0, 5, 2), (10, 0, 7, 3), (30, 1, 6, 5), (10, 3, 33, 0)])
+def test_path_length_roulette_and_chunking(B200Scene, port, max_len, roulette, spp, chunk):
+    """Path-length 1 (camera ray only), roulette from the first bounce, long paths, chunk sizes that do not divide the
+    sample count, more samples than one default chunk: default (wavefront) and megakernel against the oracle."""
+    w, h = 64, 48
+    s = scene.HostScene.builtin("box").configure(w, h, path_trace=True, samples=spp, seed=5, max_path_length=max_len,
+                                                 roulette_start_depth=roulette)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    cw = port.path_trace(s, want)
+    with B200Scene(s) as g:
+        for trav in (0, 2, 4):
+            got = base.copy()
+            g.execute(got, traversal=trav, samples_per_chunk=chunk)
+            assert_streams_identical(got, want, f"max_len={max_len} roulette={roulette} spp={spp} chunk={chunk} trav={trav}")
+            st = g.stats()
+            for k in ("closest_hit_queries", "samples", "escaped_samples"):
+                assert st[k] == cw[k], k
+
+
 def test_against_reference_build_when_present(B200Scene, ref):
     """Same comparison against the reference's own compiled kernels (oracle/_ref)."""
     s = scene.HostScene.builtin("box").configure(256, 256, path_trace=False)
