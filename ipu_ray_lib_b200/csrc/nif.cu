@@ -22,7 +22,7 @@
 #include <string>
 #include <vector>
 
-#include "nif_tc.cuh"
+#include "nif_tc_pair.cuh"
 
 namespace rt {
 
@@ -58,7 +58,7 @@ struct NifModel {
   // tensor-core path
   bool tcOk = false;
   tc::Params tc{};
-  size_t tcSmem = 0;
+  size_t tcSmem = 0, pairSmem = 0;
   std::string tcWhyNot;
 };
 
@@ -150,6 +150,30 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
     m->allocs.push_back(dw);
     cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice);
     o.wimg = (const __half*)dw;
+    // CTA-pair images: the same blocks with only the columns [r n/2, (r + 1) n/2) of each, for r = 0, 1
+    {
+      std::vector<__half> pair;
+      for (int r = 0; r < 2; ++r) {
+        img.clear();
+        block(loK, r * (o.n0 / 2), o.n0 / 2, loValue);
+        if (o.n1) block(loK, o.n0 + r * (o.n1 / 2), o.n1 / 2, loValue);
+        if (hiAct) block(hiAct, r * (o.n0 / 2), o.n0 / 2, hiValue);
+        if (hiAct && o.n1) block(hiAct, o.n0 + r * (o.n1 / 2), o.n1 / 2, hiValue);
+        if (r == 0) o.pairRankBytes = (uint32_t)(img.size() * 2);
+        pair.insert(pair.end(), img.begin(), img.end());
+      }
+      void* dp = nullptr;
+      if (cudaMalloc(&dp, pair.size() * 2) != cudaSuccess) return no("cudaMalloc failed");
+      m->allocs.push_back(dp);
+      cudaMemcpy(dp, pair.data(), pair.size() * 2, cudaMemcpyHostToDevice);
+      o.wimgPair = (const __half*)dp;
+    }
+  }
+  m->pairSmem = (size_t)(t.actPlanes + tc::kStaticPlanesMax) * tc::kPlaneBytes + (size_t)tc::kPairStages * tc::kPairStageBytes +
+                (3 * tc::kPairStages + 4) * 8 + 16;
+  if (cudaFuncSetAttribute(tc::nif_mlp_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->pairSmem) != cudaSuccess) {
+    cudaGetLastError();
+    return no("cudaFuncSetAttribute(max dynamic shared memory, pair kernel) failed");
   }
   if (cudaFuncSetAttribute(tc::nif_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tcSmem) != cudaSuccess) {
     cudaGetLastError();
@@ -334,8 +358,29 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
       cudaMemsetAsync(dProf, 0, (size_t)tcGrid * 16 * sizeof(unsigned long long), stream);
       params.prof = dProf;
     }
-    tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(params, uvDirect, slotEscape, queue, dCount, count, out);
-    const cudaError_t te = cudaGetLastError();
+    // CTA pairs (cta_group::2, nif_tc_pair.cuh): each SM streams half of the weights. Correct and parity-tested, but
+    // measured slower (39.6 K cycles per 2-tile group against 28 K per tile and SM: every layer boundary now pays the
+    // DSMEM round trips between the two epilogues and the leader), so it is opt-in: B200RT_NIF_PAIR=1.
+    static const bool usePair = [] { const char* e = std::getenv("B200RT_NIF_PAIR"); return e && e[0] == '1'; }();
+    cudaError_t te;
+    if (usePair && sms >= 2) {
+      const uint32_t groups = (tcTiles + 1u) / 2u;
+      const uint32_t pairs = groups < (uint32_t)(sms / 2) ? (groups ? groups : 1u) : (uint32_t)(sms / 2);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2u * pairs);
+      cfg.blockDim = dim3(tc::kThreads);
+      cfg.dynamicSmemBytes = m->pairSmem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      te = cudaLaunchKernelEx(&cfg, tc::nif_mlp_tc_pair_kernel, params, uvDirect, slotEscape, queue, dCount, count, out);
+    } else {
+      tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(params, uvDirect, slotEscape, queue, dCount, count, out);
+      te = cudaGetLastError();
+    }
     if (te != cudaSuccess) { g_nifError = cudaGetErrorString(te); return -1; }
     if (profile) {  // debugging aid: per-role cycle breakdown of CTA 0 (synchronises!)
       std::vector<unsigned long long> h((size_t)tcGrid * 16);
@@ -347,6 +392,7 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
       std::fprintf(stderr, "[nif profile] CTA0 of %u, rows %u:", tcGrid, count);
       const double tiles = h[tc::PF_TILES] ? (double)h[tc::PF_TILES] : 1.0;
       for (int i = 0; i < tc::PF_COUNT; ++i) std::fprintf(stderr, " %s=%.0f/tile", names[i], (double)h[i] / tiles);
+      std::fprintf(stderr, " wait peer weights=%.0f/tile", (double)h[tc::PF_COUNT] / tiles);
       std::fprintf(stderr, "\n");
     }
     if (launches) *launches += 1;
