@@ -169,6 +169,33 @@ def test_full_size_config1_shadow_trace(B200Scene, port):
         assert a.tobytes() == b.tobytes()
 
 
+def test_full_size_config2_path_trace_window(B200Scene, port):
+    """BASELINE.json config 2 geometry (1440 x 1440, path trace, seed 1442) on a 1440 x 48 window of the full frame:
+    the RNG streams and camera rays are those of the full render (they key on full-image pixel coordinates), so this is
+    a bit-exact slice of the headline workload at a size the CPU checker finishes in seconds. Also: two runs are
+    byte-identical, and 16 spp = 10 spp + 6 more."""
+    w = h = 1440
+    spp = 16
+    s = scene.HostScene.builtin("box").configure(w, h, path_trace=True, samples=spp, seed=1442)
+    base = scene.init_ray_stream(w, h, s.fov, window=(1440, 48, 0, 696))
+    assert base.size == 1440 * 48
+    want = base.copy()
+    cw = port.path_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got)
+        assert_streams_identical(got, want, "config 2 window, default path")
+        st = g.stats()
+        assert st["closest_hit_queries"] == cw["closest_hit_queries"] and st["escaped_samples"] == cw["escaped_samples"]
+        again = base.copy()
+        g.execute(again)
+        assert again.tobytes() == got.tobytes()
+        split = base.copy()
+        g.execute(split, first_sample=0, num_samples=10)
+        g.execute(split, first_sample=10, num_samples=6)
+        assert_streams_identical(split, want, "10 + 6 samples")
+
+
 def test_random_and_degenerate_queries(B200Scene, port, box_scene, spheres_scene):
     rng = np.random.default_rng(11)
     for s, lo, hi in ((box_scene, (-300, -300, -1400), (300, 300, -700)), (spheres_scene, (-4, -2, -8), (4, 3, 0))):

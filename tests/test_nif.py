@@ -136,3 +136,18 @@ def test_nif_lit_path_trace_matches_oracle(port, name, chunk):
     # per-pixel: allow the rare fp16 argument flip caused by libm-vs-CUDA acos/atan2 ulp differences
     rel = np.abs(got["rgb"] - want["rgb"]).max(axis=1) / np.maximum(np.abs(want["rgb"]).max(axis=1), 1e-6)
     assert np.mean(rel > MAX_REL) < 5e-3
+
+
+@pytest.mark.gpu
+def test_cta_pair_kernel_matches_oracle_too():
+    """The opt-in cta_group::2 kernel (B200RT_NIF_PAIR=1 is read once per process, hence the subprocess) passes the same
+    NIF parity tests, including tile counts that leave the peer CTA of the last pair without a tile."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, B200RT_NIF_PAIR="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
+                        "gpu_nif_eval_matches_oracle or nif_lit_path_trace"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
