@@ -103,7 +103,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *exc):
         if self.proc:
@@ -117,7 +123,15 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        timed = [r for t, r in self.rows if t0 is not None and t1 is not None and t0 <= t <= t1]
+        note = None
+        if not timed and self.rows:
+            # timed region shorter than one nvidia-smi period: fall back to the samples taken under the same load
+            # during the warm-up steps that precede it
+            timed = [r for _, r in self.rows]
+            note = "timed region shorter than one sampling period: samples are from the warm-up steps (same load)"
+        for r in timed:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -127,7 +141,10 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -181,7 +198,7 @@ def cpu_baseline(args, scene, nif, kind_pref=("port",), seconds=12.0):
     q = cnt["closest_hit_queries"] + cnt["occlusion_queries"]
     return {
         "value": q / dt / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-        "samples_per_s": cnt["samples"] / dt,
+        "samples_per_s": cnt["samples"] / dt, "seconds": dt,
         "sample": f"{npix} pixels (every {stride}th of the {w}x{h} frame) x {spp} spp = {cnt['samples']} samples, "
                   f"{q} BVH queries in {dt:.2f} s; OpenMP dynamic schedule over rays, per-(pixel,sample) RNG streams"
                   + ("; NIF evaluated in fp32 on the CPU for escaped rays" if use_nif is not None else
@@ -206,7 +223,9 @@ def run_reference(args):
     sps = float(np.mean([b["samples_per_s"] for b in vals]))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": float(np.mean([b["seconds"] for b in vals])) * 1e3,
+        "ms_per_full_step_extrapolated": args.width * args.height * args.samples / sps * 1e3,
+        "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, args.gpus),
         "samples_per_s": sps,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": base["cores"], "kind": base["kind"], "sample": base["sample"]},
@@ -287,16 +306,18 @@ def run_b200(args):
             totals["kernel_ms"] += st["kernel_ms"]
 
     # ---- device-resident arm ----
-    for _ in range(args.warmup):
-        device_step(False)
-    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank) as clocks:  # started before the warm-up so that it is running when the clock starts
+        for _ in range(args.warmup):
+            device_step(False)
+        barrier()
+        clocks.mark_start()
         ev0.record()
         for _ in range(args.steps):
             device_step(True)
         ev1.record()
         barrier()
+        clocks.mark_end()
     dev_ms = ev0.elapsed_time(ev1)
 
     # ---- end-to-end arm: host buffers through b200rt_trace ----
