@@ -452,9 +452,12 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
           launches += (uint64_t)nifLaunches;
         }
         if (!slots) continue;  // path tracer without an environment light: rgb was accumulated in the kernel
-        const uint32_t threads = 256, blocks = (uint32_t)((n + threads - 1) / threads);
+        const uint32_t threads = 256, blocks = (uint32_t)((n + rt::kAccPixels - 1) / rt::kAccPixels);
+        const size_t accSmem = (size_t)rt::kAccPixels * (c * 7u + 1u) * sizeof(float);
+        if (accSmem > 48 * 1024)
+          CU_TRY(cudaFuncSetAttribute(rt::wf_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)accSmem));
         timer.begin(KernelTimer::ACCUM, sc.stream);
-        rt::wf_accumulate_kernel<<<blocks, threads, 0, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,
+        rt::wf_accumulate_kernel<<<blocks, threads, accSmem, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,
                                                                     (const float*)sc.slotEscape.p,
                                                                     sc.nif ? (const float*)sc.slotEnv.p : nullptr);
         timer.end(sc.stream);

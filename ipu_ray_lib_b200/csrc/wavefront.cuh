@@ -384,25 +384,51 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
 }
 
 // rgb += colour_s (+ throughput_s * env_s when an environment light is loaded), s in chunk order.
-__global__ void wf_accumulate_kernel(float* rays, uint32_t numRays, uint32_t chunk, const float* slotColor,
-                                     const float* slotEscape, const float* slotEnv) {
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= numRays) return;
-  float* tr = rays + (size_t)idx * TR_WORDS;
-  V3 rgb = mk(tr[TR_RGB], tr[TR_RGB + 1], tr[TR_RGB + 2]);
-  for (uint32_t c = 0; c < chunk; ++c) {
-    const size_t slot = (size_t)idx * chunk + c;
-    const float* col = slotColor + 3 * slot;
-    rgb = rgb + mk(col[0], col[1], col[2]);
+//
+// The slot arrays are [pixel][sample]: a thread that walks its pixel's samples reads with a stride of chunk * 12 B
+// between lanes. So a block first turns the slots of its kAccPixels pixels into the two addends of every sample
+// (colour, throughput * env) with fully coalesced loads, parks them in shared memory, and only then does each thread
+// add up its pixel's row -- in the same order and with the same operations as the sequential loop.
+constexpr int kAccPixels = 64;
+__global__ void __launch_bounds__(256) wf_accumulate_kernel(float* rays, uint32_t numRays, uint32_t chunk, const float* slotColor,
+                                                           const float* slotEscape, const float* slotEnv) {
+  extern __shared__ float accSmem[];  // [kAccPixels][chunk * 7 + 1]: per sample colour.xyz, (throughput * env).xyz, lit flag
+  const uint32_t rowWords = chunk * 7u + 1u;  // odd stride: the per-pixel walk below is bank-conflict free
+  const uint32_t pix0 = blockIdx.x * kAccPixels;
+  const uint32_t pixels = min((uint32_t)kAccPixels, numRays - pix0);
+  const uint32_t slots = pixels * chunk;
+  const size_t slot0 = (size_t)pix0 * chunk;
+  for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) {
+    const uint32_t pl = i / chunk, c = i - pl * chunk;
+    float* dst = accSmem + pl * rowWords + c * 7u;
+    const float* col = slotColor + 3 * (slot0 + i);
+    dst[0] = col[0]; dst[1] = col[1]; dst[2] = col[2];
+    float ex = 0.f, ey = 0.f, ez = 0.f;
+    bool lit = false;
     if (slotEnv) {
-      const float* se = slotEscape + 5 * slot;
+      const float* se = slotEscape + 5 * (slot0 + i);
       if (se[3] >= 0.f) {
-        const float* env = slotEnv + 3 * slot;
-        rgb = rgb + mk(se[0], se[1], se[2]) * mk(env[2], env[1], env[0]);
+        const float* env = slotEnv + 3 * (slot0 + i);
+        const V3 e = mk(se[0], se[1], se[2]) * mk(env[2], env[1], env[0]);
+        ex = e.x; ey = e.y; ez = e.z;
+        lit = true;
       }
     }
+    // a sample without an environment term must not add anything (not even +0: -0 + 0 would flip a sign bit)
+    dst[3] = ex; dst[4] = ey; dst[5] = ez; dst[6] = lit ? 1.f : 0.f;
   }
-  tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z;
+  __syncthreads();
+  if (threadIdx.x < pixels) {
+    float* tr = rays + (size_t)(pix0 + threadIdx.x) * TR_WORDS;
+    V3 rgb = mk(tr[TR_RGB], tr[TR_RGB + 1], tr[TR_RGB + 2]);
+    const float* row = accSmem + threadIdx.x * rowWords;
+    for (uint32_t c = 0; c < chunk; ++c) {
+      const float* a = row + c * 7u;
+      rgb = rgb + mk(a[0], a[1], a[2]);
+      if (a[6] != 0.f) rgb = rgb + mk(a[3], a[4], a[5]);
+    }
+    tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z;
+  }
 }
 
 }  // namespace rt
