@@ -445,12 +445,13 @@ def rooflines(prof, peaks, n_local, spp, flops_per_lookup, sm_mhz=None):
          "traffic": (traffic.get("nif_mlp_kernel") or {}).get("dram_bytes_per_launch"), "traffic_unit": unit_note},
     ]
     if wavefront:
-        # wf_generate + wf_shade: HBM-bound on the path record. Algorithmic bytes per path-bounce: 84 B read (queue id,
-        # hit, origin, direction, throughput, RNG) + 68 B written for the ~70 % that survive; 80 B per path at generate.
+        # wf_shade: HBM-bound on the path record. Algorithmic bytes per path-bounce: 84 B read (queue id, hit, origin,
+        # direction, throughput, RNG; only the 16 B hit at bounce 0, whose camera ray is recomputed) + 68 B written for
+        # the ~70 % that survive (+ the 12 B colour slot at bounce 0).
         shade_s = max(prof["shade_kernel_ms"] * 1e-3, 1e-9)
-        shade_bytes = prof["queries"] * (84.0 + 0.7 * 68.0) + prof["samples"] * 80.0
+        shade_bytes = (prof["queries"] - prof["samples"]) * 84.0 + prof["samples"] * (16.0 + 12.0) + prof["queries"] * 0.7 * 68.0
         sl = max(prof["shade_kernel_launches"], 1)
-        kernels.append({"kernel": "wf_shade_kernel (+ wf_generate)", "bound": "hbm", "share_of_step": shade_s / step_s,
+        kernels.append({"kernel": "wf_shade_kernel", "bound": "hbm", "share_of_step": shade_s / step_s,
                         "launches_per_step": prof["shade_kernel_launches"], "avg_launch_ms": shade_s * 1e3 / sl,
                         "algorithmic_bytes_per_launch": shade_bytes / sl, "achieved": shade_bytes / shade_s / 1e9,
                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": shade_bytes / shade_s / 1e9 / peaks["hbm_gbs"],

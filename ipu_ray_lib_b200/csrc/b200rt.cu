@@ -409,24 +409,22 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
           const int wfBlock = envWfThreads > 0 ? std::min(envWfThreads, 1024) : (L.shared ? 1024 : L.block);
           const int wfGrid = L.shared ? L.grid : sc.numSMs * (1024 / L.block);
           CU_TRY(cudaMemsetAsync(sc.wfCounts.p, 0, 16, sc.stream));
-          timer.begin(KernelTimer::SHADE, sc.stream);
-          rt::wf_generate_kernel<<<gridSmall, 256, 0, sc.stream>>>(w);
-          timer.end(sc.stream);
-          CU_TRY(cudaGetLastError());
-          launches += 1;
           for (uint32_t b = 0; b < sc.desc.max_path_length; ++b) {
             w.qIn = (int)(b & 1u);
             CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + 2, 0, 4, sc.stream));            // fetch cursor
             CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + (w.qIn ^ 1), 0, 4, sc.stream));  // next queue size
+            const bool first = b == 0;  // bounce 0: camera rays are generated in the kernels, the queue is the identity
             timer.begin(KernelTimer::TRACE, sc.stream);
             {
               cudaError_t e;
               if (L.shared) {
-                auto k = L.count ? rt::wf_trace_kernel<true, true> : rt::wf_trace_kernel<true, false>;
+                auto k = L.count ? (first ? rt::wf_trace_kernel<true, true, true> : rt::wf_trace_kernel<true, true, false>)
+                                 : (first ? rt::wf_trace_kernel<true, false, true> : rt::wf_trace_kernel<true, false, false>);
                 e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
                 if (e == cudaSuccess) { k<<<wfGrid, wfBlock, L.smem, sc.stream>>>(w); e = cudaGetLastError(); }
               } else {
-                auto k = L.count ? rt::wf_trace_kernel<false, true> : rt::wf_trace_kernel<false, false>;
+                auto k = L.count ? (first ? rt::wf_trace_kernel<false, true, true> : rt::wf_trace_kernel<false, true, false>)
+                                 : (first ? rt::wf_trace_kernel<false, false, true> : rt::wf_trace_kernel<false, false, false>);
                 k<<<wfGrid, L.block, 0, sc.stream>>>(w);
                 e = cudaGetLastError();
               }
@@ -434,8 +432,13 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
             }
             timer.end(sc.stream);
             timer.begin(KernelTimer::SHADE, sc.stream);
-            if (sc.nif) rt::wf_shade_kernel<true><<<gridSmall, 256, 0, sc.stream>>>(w);
-            else rt::wf_shade_kernel<false><<<gridSmall, 256, 0, sc.stream>>>(w);
+            if (sc.nif) {
+              if (first) rt::wf_shade_kernel<true, true><<<gridSmall, 256, 0, sc.stream>>>(w);
+              else rt::wf_shade_kernel<true, false><<<gridSmall, 256, 0, sc.stream>>>(w);
+            } else {
+              if (first) rt::wf_shade_kernel<false, true><<<gridSmall, 256, 0, sc.stream>>>(w);
+              else rt::wf_shade_kernel<false, false><<<gridSmall, 256, 0, sc.stream>>>(w);
+            }
             timer.end(sc.stream);
             CU_TRY(cudaGetLastError());
             launches += 2;

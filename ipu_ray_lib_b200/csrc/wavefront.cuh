@@ -4,8 +4,8 @@
 // slowest traversal: with ~10 inner-node steps on average and a long tail, ncu measured ~8 of 32 lanes active in the
 // traversal loop. Here the per-path state lives in HBM between bounces and three kernels split the work:
 //
-//   wf_generate  one thread per (pixel, sample) of the chunk: per-(pixel,sample) RNG stream, jittered camera ray,
-//                first offsetRay; all paths enter queue 0
+//   (bounce 0)   no generate kernel: the first trace and shade kernels compute the camera ray of path p = (pixel, sample)
+//                themselves (per-(pixel,sample) RNG stream, jitter, first offsetRay) and treat the queue as the identity
 //   wf_trace     persistent warps; every lane pulls ray ids from the bounce's queue ON ITS OWN and pulls the next one
 //                the moment its traversal ends, so lanes never wait for a neighbour's long traversal; inside, each
 //                warp iteration runs one phase chosen by ballot (inner-node steps while enough lanes want one, else
@@ -49,49 +49,32 @@ struct WfArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) wf_generate_kernel(const WfArgs a) {
+// Start of path p = (pixel idx, sample c of the chunk): per-(pixel,sample) RNG stream, jittered camera ray and the first
+// offsetRay of the bounce loop (trace.cpp:126). There is no generate kernel: the bounce-0 trace kernel and the bounce-0
+// shade kernel both call this (a few hundred instructions) instead of writing and re-reading 80 B per path.
+__device__ __forceinline__ void wf_camera_path(const WfArgs& a, uint32_t p, V3& o, V3& d, Rng& rng) {
   const TraceArgs& t = a.t;
-  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < a.numPaths; p += gridDim.x * blockDim.x) {
-    const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
-    const uint32_t s = t.firstSample + c;
-    const float* tr = t.rays + (size_t)idx * TR_WORDS;
-    const float row = tr[TR_ROW], col = tr[TR_COL];
-    const uint32_t pixelIndex = (uint32_t)row * (uint32_t)t.imageWidth + (uint32_t)col;
-    // sampleCameraRays (codelets/TraceCodelets.cpp:142-164) with the per-(pixel,sample) stream
-    Rng rng;
-    rng_seed_stream(rng, t.rngKey, pixelIndex, s);
-    const uint64_t ra = rng_next(rng), rb = rng_next(rng);
-    float g0, g1;
-    gaussian_pair(ra, rb, g0, g1);
-    const float pu = row + t.antiAlias * g0;
-    const float pv = col + t.antiAlias * g1;
-    const V3 d = pixel_to_ray_dir(pv, pu, t.imageWidth, t.imageHeight, t.tanTheta);
-    const V3 n = mk(0.f, 0.f, 1.f);
-    const V3 o = offset_origin(mk(0.f, 0.f, 0.f), d, n);  // first offsetRay of the bounce loop (trace.cpp:126)
-    a.b.rayO[p] = make_float4(o.x, o.y, o.z, __uint_as_float(kInvalidGeom << 16));  // bounce 0, no flags
-    a.b.rayD[p] = make_float4(d.x, d.y, d.z, __uint_as_float(kInvalidPrim));
-    a.b.thr[p] = make_float4(1.f, 1.f, 1.f, __int_as_float(0x7f800000));
-    a.b.rng[p] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
-    if (s == a.lastSample) a.b.nrm[p] = make_float4(n.x, n.y, n.z, 0.f);
-    float* sc3 = t.slotColor + 3 * (size_t)p;
-    sc3[0] = 0.f; sc3[1] = 0.f; sc3[2] = 0.f;
-    a.b.queue[0][p] = p;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[0] = a.numPaths;
+  const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
+  const float* tr = t.rays + (size_t)idx * TR_WORDS;
+  const float row = tr[TR_ROW], col = tr[TR_COL];
+  const uint32_t pixelIndex = (uint32_t)row * (uint32_t)t.imageWidth + (uint32_t)col;
+  d = camera_ray(t, row, col, pixelIndex, t.firstSample + c, rng);
+  o = offset_origin(mk(0.f, 0.f, 0.f), d, mk(0.f, 0.f, 1.f));
 }
 
 // ------------------------------------------------------------------------------------------------
 enum : int { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2, WF_DONE = 3 };
 
-template <bool kShared, bool kCount>
+template <bool kShared, bool kCount, bool kFirst>
 __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const uint2* nodes = stage_nodes<kShared>(a.t, reinterpret_cast<uint2*>(smemRaw));
   const DevScene& sc = a.t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
   const float inf = __int_as_float(0x7f800000);
+  // bounce 0 (kFirst): the queue is the identity over all paths of the chunk and the rays are the camera rays
   const uint32_t* queue = a.b.queue[a.qIn];
-  const uint32_t count = a.b.counts[a.qIn];
+  const uint32_t count = kFirst ? a.numPaths : a.b.counts[a.qIn];
   uint32_t* cursor = a.b.counts + 2;
   Counters cnt = {0u, 0u};
   unsigned nClosest = 0;
@@ -196,10 +179,16 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
           path = 0xFFFFFFFFu;
           phase = WF_DONE;
         } else {
-          path = queue[qi];
-          const float4 ro = a.b.rayO[path], rd = a.b.rayD[path];
-          o = mk(ro.x, ro.y, ro.z);
-          d = mk(rd.x, rd.y, rd.z);
+          if (kFirst) {
+            path = qi;
+            Rng unused;
+            wf_camera_path(a, path, o, d, unused);
+          } else {
+            path = queue[qi];
+            const float4 ro = a.b.rayO[path], rd = a.b.rayD[path];
+            o = mk(ro.x, ro.y, ro.z);
+            d = mk(rd.x, rd.y, rd.z);
+          }
           // start of CompactBvh::intersect (tMin = 0, tMax = inf as set by the bounce loop, trace.cpp:128-130)
           nClosest++;
           inv = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
@@ -224,14 +213,14 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool kNif>
+template <bool kNif, bool kFirst>
 __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
   const TraceArgs& t = a.t;
   const DevScene& sc = t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
   const uint32_t* queueIn = a.b.queue[a.qIn];
   uint32_t* queueOut = a.b.queue[a.qIn ^ 1];
-  const uint32_t count = a.b.counts[a.qIn];
+  const uint32_t count = kFirst ? a.numPaths : a.b.counts[a.qIn];
   uint32_t* countOut = a.b.counts + (a.qIn ^ 1);
   unsigned nSamples = 0, nEscaped = 0;
   __shared__ uint32_t sCount[2][8];
@@ -245,10 +234,8 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
     bool survive = false;
     uint32_t appendSlot = 0xFFFFFFFFu, p = 0;
     if (valid) {
-      p = queueIn[i];
+      p = kFirst ? i : queueIn[i];
       const float4 ha = a.b.hitA[p];
-      const float4 ro = a.b.rayO[p], rd = a.b.rayD[p], th = a.b.thr[p];
-      const uint4 rs = a.b.rng[p];
       Hit hit;
       hit.t = ha.x; hit.geomID = __float_as_uint(ha.y); hit.primID = __float_as_uint(ha.z); hit.tri = __float_as_uint(ha.w);
       hit.node = 0; hit.b0 = hit.b1 = hit.b2 = 0.f;
@@ -256,17 +243,25 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
       const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
       const uint32_t s = t.firstSample + c;
       const bool lastOne = s == a.lastSample;  // this path's HitRecord is the one left in the ray stream
-      V3 o = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z), n = mk(0.f, 0.f, 1.f);
-      if (lastOne) { const float4 nn = a.b.nrm[p]; n = mk(nn.x, nn.y, nn.z); }
-      V3 thr = mk(th.x, th.y, th.z);
+      V3 o, d, n = mk(0.f, 0.f, 1.f), thr = mk(1.f, 1.f, 1.f);
+      uint32_t bounce = 0, flags = 0, geomID = kInvalidGeom, primID = kInvalidPrim;
+      Rng rng;
+      if (kFirst) {
+        wf_camera_path(a, p, o, d, rng);  // same ray, same RNG state as the trace kernel started from
+      } else {
+        const float4 ro = a.b.rayO[p], rd = a.b.rayD[p], th = a.b.thr[p];
+        const uint4 rs = a.b.rng[p];
+        o = mk(ro.x, ro.y, ro.z); d = mk(rd.x, rd.y, rd.z);
+        if (lastOne) { const float4 nn = a.b.nrm[p]; n = mk(nn.x, nn.y, nn.z); }
+        thr = mk(th.x, th.y, th.z);
+        const uint32_t packed = __float_as_uint(ro.w);
+        bounce = packed & 0xffu; flags = (packed >> 8) & 0xffu; geomID = packed >> 16;
+        primID = __float_as_uint(rd.w);
+        rng.s0 = (uint64_t)rs.x | ((uint64_t)rs.y << 32);
+        rng.s1 = (uint64_t)rs.z | ((uint64_t)rs.w << 32);
+      }
       V3 emitted = mk(0.f, 0.f, 0.f);  // thr * emission picked up at this bounce
       bool gotEmission = false, poisoned = false;
-      const uint32_t packed = __float_as_uint(ro.w);
-      uint32_t bounce = packed & 0xffu, flags = (packed >> 8) & 0xffu, geomID = packed >> 16;
-      uint32_t primID = __float_as_uint(rd.w);
-      Rng rng;
-      rng.s0 = (uint64_t)rs.x | ((uint64_t)rs.y << 32);
-      rng.s1 = (uint64_t)rs.z | ((uint64_t)rs.w << 32);
       if (bounce == 0) nSamples++;
 
       // ---- rest of one bounce-loop iteration (trace.cpp:133-184) ----
@@ -312,9 +307,9 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
       }
 
       // running colour of the path: color = color + thr * emission, then (unknown material) color = color * NaN
-      if (gotEmission || poisoned) {
+      if (kFirst || gotEmission || poisoned) {
         float* sc3 = t.slotColor + 3 * (size_t)p;
-        V3 color = mk(sc3[0], sc3[1], sc3[2]);
+        V3 color = kFirst ? mk(0.f, 0.f, 0.f) : mk(sc3[0], sc3[1], sc3[2]);
         if (gotEmission) color = color + emitted;
         if (poisoned) color = color * __int_as_float(0x7fc00000);
         sc3[0] = color.x; sc3[1] = color.y; sc3[2] = color.z;
