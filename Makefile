@@ -23,7 +23,7 @@ $(CSRC)/b200rt.o: $(CSRC)/b200rt.cu $(CSRC)/trace_kernels.cuh $(CSRC)/path_trace
                   $(CSRC)/sin_deg_table.inc $(CSRC)/nif.cuh include/b200rt.h
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(CSRC)/nif.o: $(CSRC)/nif.cu $(CSRC)/nif.cuh $(CSRC)/nif_tc.cuh $(CSRC)/nif_tc_pair.cuh include/b200rt.h
+$(CSRC)/nif.o: $(CSRC)/nif.cu $(CSRC)/nif.cuh $(CSRC)/nif_tc.cuh $(CSRC)/nif_tc_pair.cuh $(CSRC)/nif_tc_pair2.cuh include/b200rt.h
 	$(NVCC) $(NVFLAGS_NIF) -c -o $@ $<
 
 $(PKG)/libb200rt.so: $(CSRC)/b200rt.o $(CSRC)/nif.o

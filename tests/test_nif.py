@@ -139,14 +139,16 @@ def test_nif_lit_path_trace_matches_oracle(port, name, chunk):
 
 
 @pytest.mark.gpu
-def test_cta_pair_kernel_matches_oracle_too():
-    """The opt-in cta_group::2 kernel (B200RT_NIF_PAIR=1 is read once per process, hence the subprocess) passes the same
-    NIF parity tests, including tile counts that leave the peer CTA of the last pair without a tile."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_cta_pair_kernels_match_oracle_too(mode):
+    """The opt-in cta_group::2 kernels (B200RT_NIF_PAIR=1: pair version of the product kernel, 2: pair + fully overlapped
+    pipeline; read once per process, hence the subprocess) pass the same NIF parity tests, including tile counts that
+    leave the peer CTA of the last pair without a tile."""
     import os
     import subprocess
     import sys
 
-    env = dict(os.environ, B200RT_NIF_PAIR="1")
+    env = dict(os.environ, B200RT_NIF_PAIR=mode)
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
                         "gpu_nif_eval_matches_oracle or nif_lit_path_trace"], env=env, capture_output=True, text=True,
                        timeout=600)
