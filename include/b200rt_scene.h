@@ -63,6 +63,15 @@ typedef struct b200rt_nif_metadata {
 } b200rt_nif_metadata;
 int  b200rt_read_nif_metadata(const char* path, b200rt_nif_metadata* out);
 
+/* The reference's serialised scene: `SceneRef` written by Serialiser<16> (include/serialisation/Serialiser.hpp:24-64,
+ * serialisation.hpp:34-52) -- the byte stream IpuScene uploads (src/IpuScene.cpp:52, :665) and the device reads back
+ * in place (deserialisation.hpp:29-59). b200rt_scene_desc_from_blob fills `out` with pointers INTO `blob` (zero copy:
+ * the blob must outlive the desc and be 16-byte aligned, like the reference's buffer). The stream carries neither the
+ * spheres / discs nor rng_seed, path_trace, device (src/IpuScene.cpp:208-215): those fields are left zero for the
+ * caller. b200rt_scene_blob_write is the matching writer; it returns the size and writes when `cap` suffices. */
+int    b200rt_scene_desc_from_blob(const void* blob, size_t bytes, b200rt_scene_desc* out);
+size_t b200rt_scene_blob_write(const b200rt_scene_desc* scene, void* out, size_t cap);
+
 /* Host sincos used for tan(fov/2) (ext/math/sincos.cpp:236); exported for tests. */
 void b200rt_sincos(float x, float* s, float* c);
 

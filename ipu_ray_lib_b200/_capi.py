@@ -133,6 +133,7 @@ B200RT_SCENE_SYMBOLS = [
     "b200rt_host_scene_desc", "b200rt_scene_last_error", "b200rt_build_bvh",
     "b200rt_init_ray_stream", "b200rt_scale_rgb", "b200rt_visualise_hits",
     "b200rt_write_exr", "b200rt_write_pfm", "b200rt_read_nif_metadata", "b200rt_sincos",
+    "b200rt_scene_desc_from_blob", "b200rt_scene_blob_write",
 ]
 
 _lib = None
@@ -202,6 +203,9 @@ def scene_lib() -> C.CDLL:
         L.b200rt_write_pfm.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         L.b200rt_read_nif_metadata.argtypes = [C.c_char_p, C.POINTER(NifMetadata)]
         L.b200rt_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.b200rt_scene_desc_from_blob.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(SceneDesc)]
+        L.b200rt_scene_blob_write.argtypes = [C.POINTER(SceneDesc), C.c_void_p, C.c_size_t]
+        L.b200rt_scene_blob_write.restype = C.c_size_t
         L.b200rt_sincos.restype = None
         _scene_lib = L
     return _scene_lib

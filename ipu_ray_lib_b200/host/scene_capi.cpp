@@ -32,6 +32,54 @@ static int guarded(F&& f) {
   }
 }
 
+// ---- the reference's serialised SceneRef ----------------------------------------------------------------------
+namespace {
+// Every object sits at its own alignment relative to a 16-byte aligned base (Serialiser::calculatePadding).
+struct BlobCursor {
+  const unsigned char* base;
+  size_t size, at = 0;
+  void align(size_t a) {
+    const size_t rem = (16 + at) % a;
+    if (rem) at += a - rem;
+  }
+  template <class T> T scalar() {
+    align(alignof(T));
+    if (at + sizeof(T) > size) throw std::runtime_error("serialised scene is truncated");
+    T v;
+    std::memcpy(&v, base + at, sizeof(T));
+    at += sizeof(T);
+    return v;
+  }
+  const void* array(uint32_t& count, size_t elemSize, size_t elemAlign) {
+    count = scalar<uint32_t>();
+    align(elemAlign);
+    if (at + (size_t)count * elemSize > size) throw std::runtime_error("serialised scene is truncated");
+    const void* p = base + at;
+    at += (size_t)count * elemSize;
+    return p;
+  }
+};
+struct BlobSink {
+  unsigned char* out;
+  size_t cap, at = 0;
+  void put(const void* src, size_t n) {
+    if (out && at + n <= cap) std::memcpy(out + at, src, n);
+    at += n;
+  }
+  void align(size_t a) {
+    static const unsigned char zeros[16] = {0};
+    const size_t rem = (16 + at) % a;
+    if (rem) put(zeros, a - rem);
+  }
+  template <class T> void scalar(const T& v) { align(alignof(T)); put(&v, sizeof(T)); }
+  void array(const void* data, uint32_t count, size_t elemSize, size_t elemAlign) {
+    scalar(count);
+    align(elemAlign);
+    put(data, (size_t)count * elemSize);
+  }
+};
+}  // namespace
+
 extern "C" {
 
 const char* b200rt_scene_last_error(void) { return g_err.c_str(); }
@@ -160,6 +208,56 @@ int b200rt_read_nif_metadata(const char* path, b200rt_nif_metadata* out) {
       if (tok.str == "--layer-size") next = true;
     }
   });
+}
+
+int b200rt_scene_desc_from_blob(const void* blob, size_t bytes, b200rt_scene_desc* out) {
+  return guarded([&] {
+    if (!blob || !out) throw std::runtime_error("null argument");
+    if (reinterpret_cast<uintptr_t>(blob) % 16) throw std::runtime_error("serialised scene must be 16-byte aligned");
+    BlobCursor c{static_cast<const unsigned char*>(blob), bytes};
+    b200rt_scene_desc d{};
+    d.geometry = c.array(d.num_geometry, sizeof(GeomRef), alignof(GeomRef));
+    d.mesh_info = c.array(d.num_meshes, sizeof(MeshInfo), alignof(MeshInfo));
+    d.mesh_tris = c.array(d.num_tris, sizeof(Triangle), alignof(Triangle));
+    d.mesh_verts = c.array(d.num_verts, sizeof(Vec3), alignof(Vec3));
+    d.mesh_normals = c.array(d.num_normals, sizeof(Vec3), alignof(Vec3));
+    d.mat_ids = static_cast<const uint32_t*>(c.array(d.num_mat_ids, 4, 4));
+    d.materials = c.array(d.num_materials, sizeof(Material), alignof(Material));
+    d.bvh_nodes = c.array(d.num_bvh_nodes, sizeof(BvhNode), 4);  // CompactBVH2Node: 4-byte aligned in the stream
+    d.max_leaf_depth = c.scalar<uint32_t>();
+    d.image_width = c.scalar<float>();
+    d.image_height = c.scalar<float>();
+    d.fov_radians = c.scalar<float>();
+    d.anti_alias_scale = c.scalar<float>();
+    d.max_path_length = c.scalar<uint32_t>();
+    d.roulette_start_depth = c.scalar<uint32_t>();
+    d.samples_per_pixel = c.scalar<uint32_t>();
+    if (c.at != bytes) throw std::runtime_error("serialised scene has trailing bytes");
+    d.device = -1;
+    *out = d;
+  });
+}
+
+size_t b200rt_scene_blob_write(const b200rt_scene_desc* d, void* out, size_t cap) {
+  if (!d) return 0;
+  BlobSink w{static_cast<unsigned char*>(out), cap};
+  w.array(d->geometry, d->num_geometry, sizeof(GeomRef), alignof(GeomRef));
+  w.array(d->mesh_info, d->num_meshes, sizeof(MeshInfo), alignof(MeshInfo));
+  w.array(d->mesh_tris, d->num_tris, sizeof(Triangle), alignof(Triangle));
+  w.array(d->mesh_verts, d->num_verts, sizeof(Vec3), alignof(Vec3));
+  w.array(d->mesh_normals, d->num_normals, sizeof(Vec3), alignof(Vec3));
+  w.array(d->mat_ids, d->num_mat_ids, 4, 4);
+  w.array(d->materials, d->num_materials, sizeof(Material), alignof(Material));
+  w.array(d->bvh_nodes, d->num_bvh_nodes, sizeof(BvhNode), 4);
+  w.scalar(d->max_leaf_depth);
+  w.scalar(d->image_width);
+  w.scalar(d->image_height);
+  w.scalar(d->fov_radians);
+  w.scalar(d->anti_alias_scale);
+  w.scalar(d->max_path_length);
+  w.scalar(d->roulette_start_depth);
+  w.scalar(d->samples_per_pixel);
+  return w.at;
 }
 
 void b200rt_sincos(float x, float* s, float* c) { rt::sincos_tbl(x, *s, *c); }

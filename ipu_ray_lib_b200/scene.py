@@ -102,6 +102,44 @@ class HostScene:
                 "bvh_bytes": d.num_bvh_nodes * 24, "max_leaf_depth": d.max_leaf_depth}
 
 
+class BlobScene:
+    """A scene described by the reference's serialised ``SceneRef`` byte stream (zero copy: ``desc`` points into the
+    blob). Spheres / discs travel beside the stream, as in the reference (src/IpuScene.cpp:208-215)."""
+
+    def __init__(self, blob: np.ndarray, spheres=None, discs=None, *, path_trace: bool = True, seed: int = 1442,
+                 device: int = -1):
+        raw = np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob.view(np.uint8).ravel()
+        self._store = np.zeros(raw.size + 16, dtype=np.uint8)  # own 16-byte aligned copy
+        off = (-self._store.ctypes.data) % 16
+        self.blob = self._store[off:off + raw.size]
+        self.blob[:] = raw
+        self.desc = capi.SceneDesc()
+        rc = capi.scene_lib().b200rt_scene_desc_from_blob(capi.ptr(self.blob), self.blob.size, C.byref(self.desc))
+        if rc != 0:
+            raise RuntimeError(capi.scene_lib().b200rt_scene_last_error().decode())
+        self.spheres = np.ascontiguousarray(spheres if spheres is not None else np.zeros((0, 4)), dtype=np.float32)
+        self.discs = np.ascontiguousarray(discs if discs is not None else np.zeros((0, 7)), dtype=np.float32)
+        d = self.desc
+        d.spheres = self.spheres.ctypes.data if self.spheres.size else None
+        d.num_spheres = self.spheres.shape[0]
+        d.discs = self.discs.ctypes.data if self.discs.size else None
+        d.num_discs = self.discs.shape[0]
+        d.path_trace, d.rng_seed, d.device = int(path_trace), seed, device
+
+    @property
+    def fov(self) -> float:
+        return self.desc.fov_radians
+
+
+def scene_blob(scene) -> np.ndarray:
+    """Serialise ``scene.desc`` the way the reference's ``Serialiser<16>`` does."""
+    lib = capi.scene_lib()
+    n = lib.b200rt_scene_blob_write(C.byref(scene.desc), None, 0)
+    out = np.zeros(n, dtype=np.uint8)
+    lib.b200rt_scene_blob_write(C.byref(scene.desc), capi.ptr(out), n)
+    return out
+
+
 def init_ray_stream(width: int, height: int, fov: float, window=None) -> np.ndarray:
     """initPerspectiveRayStream + zeroRgb (src/app_utils.cpp:19-53); window = (w, h, col, row)."""
     w, h, c, r = window if window is not None else (width, height, 0, 0)

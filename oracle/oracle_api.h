@@ -70,6 +70,10 @@ int ORC(nif_eval)(const b200rt_nif_desc* nif, const float* uv, size_t n, float* 
 /* Equirect (u,v) of a direction (codelets/TraceCodelets.cpp:337-348); port only. */
 void ORC(dir_to_uv)(const float* dirs, size_t n, float rotation_radians, float* uv_out);
 
+/* SceneRef serialised with Serialiser<16> (include/serialisation/serialisation.hpp:34-52): the byte stream the reference
+ * uploads to the device (src/IpuScene.cpp:52, :665). Returns the size; writes it when cap is large enough. */
+size_t ORC(serialise_scene)(const b200rt_scene_desc* scene, uint8_t* out, size_t cap);
+
 const char* ORC(kind)(void);  /* "port" or "reference" */
 
 #ifdef __cplusplus

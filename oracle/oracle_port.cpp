@@ -608,7 +608,52 @@ int threadsOr(int t) { return t > 0 ? t : omp_get_max_threads(); }
 
 }  // namespace
 
+// Serialiser<16> restated (include/serialisation/Serialiser.hpp:24-64, serialisation.hpp:21-52): every object is
+// padded to its own alignment relative to a 16-byte aligned base; an array is a u32 count followed by its raw elements.
+namespace {
+struct BlobWriter {
+  std::vector<uint8_t> bytes;
+  void pad(size_t align) {
+    const size_t rem = (16 + bytes.size()) % align;
+    if (rem) bytes.resize(bytes.size() + (align - rem));
+  }
+  template <class T> void scalar(const T& v) {
+    pad(alignof(T));
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(&v);
+    bytes.insert(bytes.end(), p, p + sizeof(T));
+  }
+  void array(const void* data, uint32_t count, size_t elemSize, size_t elemAlign) {
+    scalar(count);
+    pad(elemAlign);
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(data);
+    bytes.insert(bytes.end(), p, p + (size_t)count * elemSize);
+  }
+};
+}  // namespace
+
 extern "C" {
+
+size_t orc_serialise_scene(const b200rt_scene_desc* d, uint8_t* out, size_t cap) {
+  BlobWriter w;
+  w.array(d->geometry, d->num_geometry, 4, 2);       // GeomRef {u16, u8, u8}
+  w.array(d->mesh_info, d->num_meshes, 16, 4);       // MeshInfo
+  w.array(d->mesh_tris, d->num_tris, 6, 2);          // Triangle {u16 x 3}
+  w.array(d->mesh_verts, d->num_verts, 12, 4);       // Vec3fa
+  w.array(d->mesh_normals, d->num_normals, 12, 4);
+  w.array(d->mat_ids, d->num_mat_ids, 4, 4);
+  w.array(d->materials, d->num_materials, 36, 4);    // Material
+  w.array(d->bvh_nodes, d->num_bvh_nodes, 24, 4);    // CompactBVH2Node {f32 x 3, u32, f16 x 3, u16}
+  w.scalar(d->max_leaf_depth);
+  w.scalar(d->image_width);
+  w.scalar(d->image_height);
+  w.scalar(d->fov_radians);
+  w.scalar(d->anti_alias_scale);
+  w.scalar(d->max_path_length);
+  w.scalar(d->roulette_start_depth);
+  w.scalar(d->samples_per_pixel);
+  if (out && cap >= w.bytes.size()) std::memcpy(out, w.bytes.data(), w.bytes.size());
+  return w.bytes.size();
+}
 
 const char* orc_kind(void) { return "port"; }
 

@@ -28,6 +28,8 @@
 #include <memory>
 #include <vector>
 
+#include <serialisation/serialisation.hpp>
+
 using embree_utils::HitRecord;
 using embree_utils::Ray;
 using embree_utils::TraceResult;
@@ -175,6 +177,28 @@ inline float fovTan(float fovRadians) {
 }  // namespace
 
 extern "C" {
+
+size_t ref_serialise_scene(const b200rt_scene_desc* d, uint8_t* out, size_t cap) {
+  // the reference's own writer, fed a SceneRef over the caller's arrays (src/IpuScene.cpp:31, :52)
+  SceneRef ref;
+  ref.geometry = ArrayRef<GeomRef>((GeomRef*)d->geometry, d->num_geometry);
+  ref.meshInfo = ArrayRef<MeshInfo>((MeshInfo*)d->mesh_info, d->num_meshes);
+  ref.meshTris = ArrayRef<Triangle>((Triangle*)d->mesh_tris, d->num_tris);
+  ref.meshVerts = ArrayRef<Vec3fa>((Vec3fa*)d->mesh_verts, d->num_verts);
+  ref.meshNormals = ArrayRef<Vec3fa>((Vec3fa*)d->mesh_normals, d->num_normals);
+  ref.matIDs = ArrayRef<std::uint32_t>((std::uint32_t*)d->mat_ids, d->num_mat_ids);
+  ref.materials = ArrayRef<Material>((Material*)d->materials, d->num_materials);
+  ref.bvhNodes = ArrayRef<CompactBVH2Node>((CompactBVH2Node*)d->bvh_nodes, d->num_bvh_nodes);
+  ref.maxLeafDepth = d->max_leaf_depth;
+  ref.imageWidth = d->image_width; ref.imageHeight = d->image_height;
+  ref.fovRadians = d->fov_radians; ref.antiAliasScale = d->anti_alias_scale;
+  ref.maxPathLength = d->max_path_length; ref.rouletteStartDepth = d->roulette_start_depth;
+  ref.samplesPerPixel = d->samples_per_pixel;
+  Serialiser<16> ser(600 * 1024);
+  ser << ref;
+  if (out && cap >= ser.bytes.size()) std::memcpy(out, ser.bytes.data(), ser.bytes.size());
+  return ser.bytes.size();
+}
 
 const char* ref_kind(void) { return "reference"; }
 

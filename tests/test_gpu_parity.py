@@ -109,6 +109,22 @@ def test_path_length_roulette_and_chunking(B200Scene, port, max_len, roulette, s
                 assert st[k] == cw[k], k
 
 
+def test_render_from_the_serialised_scene(B200Scene, port, box_scene):
+    """The byte stream the reference uploads (Serialiser<16> of SceneRef) is enough to set the device scene up:
+    rendering from the zero-copy desc over the blob equals rendering from the arrays it was written from."""
+    from ipu_ray_lib_b200.scene import BlobScene, scene_blob
+    w, h = 80, 60
+    box_scene.configure(w, h, path_trace=True, samples=5, seed=1442)
+    base = scene.init_ray_stream(w, h, box_scene.fov)
+    want = base.copy()
+    port.path_trace(box_scene, want)
+    blob = BlobScene(scene_blob(box_scene), spheres=box_scene.spheres, discs=box_scene.discs, path_trace=True, seed=1442)
+    with B200Scene(blob) as g:
+        got = base.copy()
+        g.execute(got)
+        assert_streams_identical(got, want, "render from serialised scene")
+
+
 def test_against_reference_build_when_present(B200Scene, ref):
     """Same comparison against the reference's own compiled kernels (oracle/_ref)."""
     s = scene.HostScene.builtin("box").configure(256, 256, path_trace=False)

@@ -210,3 +210,62 @@ def test_nif_metadata_reader():
     assert md.embedding_dimension == 12 and md.hidden_size == 320 and list(md.image_shape) == [2048, 4096, 3]
     assert md.log_tone_map == 1 and abs(md.max - 3.4299468994140625) < 1e-7
     assert abs(md.mean[0] - (-2.3514461517333984 - 1e-8)) < 1e-6  # eps folded in (NifMetaData.cpp:48-53)
+
+
+# ---- the reference's serialised SceneRef (Serialiser<16>) --------------------------------------------------------
+def _oracle_blob(orc, s):
+    import ctypes as C
+
+    from ipu_ray_lib_b200 import _capi as capi
+    f = orc._f("serialise_scene")
+    f.restype = C.c_size_t
+    f.argtypes = [C.POINTER(capi.SceneDesc), C.c_void_p, C.c_size_t]
+    n = f(C.byref(s.desc), None, 0)
+    buf = np.zeros(n, np.uint8)
+    assert f(C.byref(s.desc), capi.ptr(buf), n) == n
+    return buf
+
+
+@pytest.mark.parametrize("fixture", ["box_scene", "spheres_scene", "dae_scene"])
+def test_serialised_scene_round_trip_and_matches_the_reference_writer(fixture, request, port):
+    """b200rt_scene_blob_write == the restated writer (== the reference's own Serialiser<16>, next test), and
+    b200rt_scene_desc_from_blob reads it back in place: same arrays, same scalars."""
+    from ipu_ray_lib_b200.scene import BlobScene, scene_blob
+    s = request.getfixturevalue(fixture)
+    s.configure(640, 480, samples=77, max_path_length=7, roulette_start_depth=2, anti_alias=0.5)
+    blob = scene_blob(s)
+    assert blob.tobytes() == _oracle_blob(port, s).tobytes()
+    b = BlobScene(blob, spheres=s.spheres, discs=s.discs)
+    for name in ("num_geometry", "num_meshes", "num_tris", "num_verts", "num_normals", "num_mat_ids", "num_materials",
+                 "num_bvh_nodes", "max_leaf_depth", "image_width", "image_height", "fov_radians", "anti_alias_scale",
+                 "max_path_length", "roulette_start_depth", "samples_per_pixel", "num_spheres", "num_discs"):
+        assert getattr(b.desc, name) == getattr(s.desc, name), name
+    import ctypes as C
+    for ptr, count, size in (("geometry", "num_geometry", 4), ("mesh_info", "num_meshes", 16), ("mesh_tris", "num_tris", 6),
+                             ("mesh_verts", "num_verts", 12), ("mesh_normals", "num_normals", 12),
+                             ("mat_ids", "num_mat_ids", 4), ("materials", "num_materials", 36), ("bvh_nodes", "num_bvh_nodes", 24)):
+        n = getattr(s.desc, count) * size
+        if n:
+            pa = C.cast(getattr(b.desc, ptr), C.c_void_p).value
+            pb = C.cast(getattr(s.desc, ptr), C.c_void_p).value
+            assert C.string_at(pa, n) == C.string_at(pb, n), ptr
+            assert b.blob.ctypes.data <= pa < b.blob.ctypes.data + b.blob.size  # zero copy: points into the blob
+
+
+def test_serialised_scene_is_the_reference_byte_stream(ref, port, box_scene, dae_scene):
+    for s in (box_scene, dae_scene):
+        s.configure(1440, 1440, samples=1000)
+        assert _oracle_blob(ref, s).tobytes() == _oracle_blob(port, s).tobytes()
+
+
+def test_malformed_serialised_scenes_are_rejected(box_scene):
+    from ipu_ray_lib_b200.scene import BlobScene, scene_blob
+    blob = scene_blob(box_scene)
+    with pytest.raises(RuntimeError, match="truncated"):
+        BlobScene(blob[:1000])
+    with pytest.raises(RuntimeError, match="trailing"):
+        BlobScene(np.concatenate([blob, np.zeros(8, np.uint8)]))
+    bad = blob.copy()
+    bad[:4] = 255  # absurd element count
+    with pytest.raises(RuntimeError, match="truncated"):
+        BlobScene(bad)
