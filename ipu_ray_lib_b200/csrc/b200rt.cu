@@ -121,6 +121,8 @@ int validate_desc(const b200rt_scene_desc& d) {
     return fail(B200RT_ERR_INVALID_ARG, "mesh_normals must be empty or one per vertex");
   if (d.max_leaf_depth > (uint32_t)rt::kMaxStack)
     return fail(B200RT_ERR_UNSUPPORTED, "BVH deeper than 64 levels");
+  if (d.path_trace && d.max_path_length == 0)
+    return fail(B200RT_ERR_INVALID_ARG, "max_path_length must be at least 1 for path tracing");
   const auto* mat = (const uint32_t*)d.mat_ids;
   for (uint32_t i = 0; i < d.num_geometry; ++i)
     if (mat[i] >= d.num_materials) return fail(B200RT_ERR_INVALID_ARG, "material index out of range");

@@ -73,6 +73,10 @@ def test_bad_arguments_are_rejected_with_a_message(box_scene):
     d.num_mat_ids = 3  # fewer materials than primitives: the reference throws std::logic_error
     assert lib.b200rt_scene_create(C.byref(d), C.byref(out)) == -1
     assert b"material" in lib.b200rt_last_error()
+    C.memmove(C.byref(d), C.byref(box_scene.desc), C.sizeof(d))
+    d.path_trace, d.max_path_length = 1, 0
+    assert lib.b200rt_scene_create(C.byref(d), C.byref(out)) == -1
+    assert b"max_path_length" in lib.b200rt_last_error()
     assert not out.value
 
 
