@@ -119,7 +119,7 @@ typedef struct b200rt_trace_stats {
   double   nif_kernel_ms;         /* sum over launches of the NIF MLP kernel time */
   double   accumulate_kernel_ms;  /* sum over launches of the ordered rgb accumulation kernel */
   uint64_t trace_kernel_launches, nif_kernel_launches;
-  double   shade_kernel_ms;       /* wavefront path tracer: sum over launches of the generate + shade kernels */
+  double   shade_kernel_ms;       /* wavefront path tracer: sum over launches of the shade kernels */
   uint64_t shade_kernel_launches;
 } b200rt_trace_stats;
 
