@@ -42,12 +42,12 @@ __device__ __forceinline__ uint32_t instr_desc(int m, int n) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-mma2_kernel(const __half* A, const __half* B, float* D, int iters, long long* cycles) {
+mma2_kernel(const __half* A, const __half* B, float* D, int iters, int commitEvery, long long* cycles) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sA = smem;                              // [K/8][128][8]
   unsigned char* sB = sA + (kK / 8) * kPlaneA;            // [K/8][N/2][8]
   uint64_t* bar = reinterpret_cast<uint64_t*>(sB + (kK / 8) * kPlaneB);
-  uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bar + 1);
+  uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bar + 2);
   const uint32_t rank = cluster_ctarank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -62,6 +62,7 @@ mma2_kernel(const __half* A, const __half* B, float* D, int iters, long long* cy
   }
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar + 1, 1u << 20);  // never completes: only the cost of committing onto it is measured
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -81,6 +82,15 @@ mma2_kernel(const __half* A, const __half* B, float* D, int iters, long long* cy
     const uint32_t idesc = instr_desc(2 * kRows, kN);
     t0 = clock64();
     for (int it = 0; it < iters; ++it) {
+      if (commitEvery && it % commitEvery == 0 && it) {
+        // a commit in the MMA stream, as the ring-stage release of the NIF pair kernels issues it (nobody waits on bar2)
+        asm volatile(
+            "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+            "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+                smem_u32(bar + 1)),
+            "h"((uint16_t)3)
+            : "memory");
+      }
       for (int ks = 0; ks < kK / 16; ++ks) {
         const uint64_t da = smem_desc(smem_u32(sA) + ks * 2 * kPlaneA, kPlaneA, 128);
         const uint64_t db = smem_desc(smem_u32(sB) + ks * 2 * kPlaneB, kPlaneB, 128);
@@ -136,11 +146,13 @@ int main() {
   cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2); cudaMalloc(&dD, 2 * kRows * kN * 4); cudaMalloc(&dCyc, 8);
   cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
-  const size_t smem = (kK / 8) * (kPlaneA + kPlaneB) + 64;
+  const size_t smem = (kK / 8) * (kPlaneA + kPlaneB) + 128;
   cudaFuncSetAttribute(mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int iters : {1, 1000}) {
+  for (int mode = 0; mode < 4; ++mode) {
+    const int iters = mode == 0 ? 1 : 1000;
+    const int commitEvery = mode == 2 ? 1 : (mode == 3 ? 4 : 0);  // a multicast commit every 4 / every 16 MMAs
     cudaMemset(dD, 0xff, 2 * kRows * kN * 4);
-    mma2_kernel<<<2, 128, smem>>>(dA, dB, dD, iters, dCyc);
+    mma2_kernel<<<2, 128, smem>>>(dA, dB, dD, iters, commitEvery, dCyc);
     const cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { std::printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
     std::vector<float> hD(2 * kRows * kN);
@@ -154,7 +166,7 @@ int main() {
         for (int k = 0; k < kK; ++k) ref += __half2float(hA[(size_t)r * kK + k]) * __half2float(hB[(size_t)n * kK + k]);
         if (std::fabs(ref - hD[(size_t)r * kN + n]) > 1e-3f) { if (firstBad < 0) firstBad = r * kN + n; ++bad; }
       }
-    std::printf("iters %d: %d of %d outputs wrong", iters, bad, 2 * kRows * kN);
+    std::printf("iters %d, commit every %d x 4 MMAs: %d of %d outputs wrong", iters, commitEvery, bad, 2 * kRows * kN);
     if (bad) std::printf(" (first at row %d col %d: got %g)", firstBad / kN, firstBad % kN, hD[firstBad]);
     std::printf("; %lld cycles = %.1f per MMA (M=256 across the pair, N=%d, K=16)\n", cyc, (double)cyc / (iters * (kK / 16)), kN);
   }
