@@ -342,7 +342,13 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
       launches += 1;
     } else {
       // Chunks of samples: trace -> (compacted escaped rays) NIF -> ordered accumulate.
-      uint32_t chunk = p.samples_per_chunk ? p.samples_per_chunk : 32u;
+      // Default chunk: enough samples for ~64 M paths per chunk (32 samples of a 1440 x 1440 frame), so that a GPU that
+      // owns a small shard of the stream (multi-GPU, crops) launches as few, as large kernels as one that owns it all.
+      uint32_t chunk = p.samples_per_chunk;
+      if (!chunk) {
+        chunk = 32u;
+        while (chunk < 1024u && (size_t)chunk * 2 * n <= ((size_t)64 << 20)) chunk *= 2;
+      }
       // bound the per-path arrays (slots; plus 136 B of path state in wavefront mode) to ~8 / ~20 GiB
       const bool slots = sc.nif || wavefront;  // per-sample colour / escape records handed to NIF + accumulate
       const bool primB = primaryPass && sc.dev.triNormals != nullptr;
@@ -458,11 +464,8 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
         }
         if (!slots) continue;  // path tracer without an environment light: rgb was accumulated in the kernel
         const uint32_t threads = 256, blocks = (uint32_t)((n + rt::kAccPixels - 1) / rt::kAccPixels);
-        const size_t accSmem = (size_t)rt::kAccPixels * (c * 7u + 1u) * sizeof(float);
-        if (accSmem > 48 * 1024)
-          CU_TRY(cudaFuncSetAttribute(rt::wf_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)accSmem));
         timer.begin(KernelTimer::ACCUM, sc.stream);
-        rt::wf_accumulate_kernel<<<blocks, threads, accSmem, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,
+        rt::wf_accumulate_kernel<<<blocks, threads, 0, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,
                                                                     (const float*)sc.slotEscape.p,
                                                                     sc.nif ? (const float*)sc.slotEnv.p : nullptr);
         timer.end(sc.stream);

@@ -384,46 +384,52 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
 // between lanes. So a block first turns the slots of its kAccPixels pixels into the two addends of every sample
 // (colour, throughput * env) with fully coalesced loads, parks them in shared memory, and only then does each thread
 // add up its pixel's row -- in the same order and with the same operations as the sequential loop.
-constexpr int kAccPixels = 64;
+constexpr int kAccPixels = 48;   // 48 x (32 x 7 + 1) floats = 43 KB of static shared memory
+constexpr int kAccSamples = 32;  // samples staged per pass (chunks may be much longer than that on small ray streams)
 __global__ void __launch_bounds__(256) wf_accumulate_kernel(float* rays, uint32_t numRays, uint32_t chunk, const float* slotColor,
                                                            const float* slotEscape, const float* slotEnv) {
-  extern __shared__ float accSmem[];  // [kAccPixels][chunk * 7 + 1]: per sample colour.xyz, (throughput * env).xyz, lit flag
-  const uint32_t rowWords = chunk * 7u + 1u;  // odd stride: the per-pixel walk below is bank-conflict free
+  // [kAccPixels][kAccSamples * 7 + 1]: per sample colour.xyz, (throughput * env).xyz, lit flag
+  __shared__ float accSmem[kAccPixels * (kAccSamples * 7 + 1)];
+  constexpr uint32_t rowWords = kAccSamples * 7u + 1u;  // odd stride: the per-pixel walk below is bank-conflict free
   const uint32_t pix0 = blockIdx.x * kAccPixels;
   const uint32_t pixels = min((uint32_t)kAccPixels, numRays - pix0);
-  const uint32_t slots = pixels * chunk;
-  const size_t slot0 = (size_t)pix0 * chunk;
-  for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) {
-    const uint32_t pl = i / chunk, c = i - pl * chunk;
-    float* dst = accSmem + pl * rowWords + c * 7u;
-    const float* col = slotColor + 3 * (slot0 + i);
-    dst[0] = col[0]; dst[1] = col[1]; dst[2] = col[2];
-    float ex = 0.f, ey = 0.f, ez = 0.f;
-    bool lit = false;
-    if (slotEnv) {
-      const float* se = slotEscape + 5 * (slot0 + i);
-      if (se[3] >= 0.f) {
-        const float* env = slotEnv + 3 * (slot0 + i);
-        const V3 e = mk(se[0], se[1], se[2]) * mk(env[2], env[1], env[0]);
-        ex = e.x; ey = e.y; ez = e.z;
-        lit = true;
+  float* tr = rays + (size_t)(pix0 + threadIdx.x) * TR_WORDS;
+  V3 rgb = mk(0.f, 0.f, 0.f);
+  if (threadIdx.x < pixels) rgb = mk(tr[TR_RGB], tr[TR_RGB + 1], tr[TR_RGB + 2]);
+  for (uint32_t c0 = 0; c0 < chunk; c0 += kAccSamples) {
+    const uint32_t cs = min((uint32_t)kAccSamples, chunk - c0);
+    for (uint32_t i = threadIdx.x; i < pixels * cs; i += blockDim.x) {
+      const uint32_t pl = i / cs, c = i - pl * cs;
+      const size_t slot = (size_t)(pix0 + pl) * chunk + c0 + c;
+      float* dst = accSmem + pl * rowWords + c * 7u;
+      const float* col = slotColor + 3 * slot;
+      dst[0] = col[0]; dst[1] = col[1]; dst[2] = col[2];
+      float ex = 0.f, ey = 0.f, ez = 0.f;
+      bool lit = false;
+      if (slotEnv) {
+        const float* se = slotEscape + 5 * slot;
+        if (se[3] >= 0.f) {
+          const float* env = slotEnv + 3 * slot;
+          const V3 e = mk(se[0], se[1], se[2]) * mk(env[2], env[1], env[0]);
+          ex = e.x; ey = e.y; ez = e.z;
+          lit = true;
+        }
+      }
+      // a sample without an environment term must not add anything (not even +0: -0 + 0 would flip a sign bit)
+      dst[3] = ex; dst[4] = ey; dst[5] = ez; dst[6] = lit ? 1.f : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x < pixels) {
+      const float* row = accSmem + threadIdx.x * rowWords;
+      for (uint32_t c = 0; c < cs; ++c) {
+        const float* a = row + c * 7u;
+        rgb = rgb + mk(a[0], a[1], a[2]);
+        if (a[6] != 0.f) rgb = rgb + mk(a[3], a[4], a[5]);
       }
     }
-    // a sample without an environment term must not add anything (not even +0: -0 + 0 would flip a sign bit)
-    dst[3] = ex; dst[4] = ey; dst[5] = ez; dst[6] = lit ? 1.f : 0.f;
+    __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x < pixels) {
-    float* tr = rays + (size_t)(pix0 + threadIdx.x) * TR_WORDS;
-    V3 rgb = mk(tr[TR_RGB], tr[TR_RGB + 1], tr[TR_RGB + 2]);
-    const float* row = accSmem + threadIdx.x * rowWords;
-    for (uint32_t c = 0; c < chunk; ++c) {
-      const float* a = row + c * 7u;
-      rgb = rgb + mk(a[0], a[1], a[2]);
-      if (a[6] != 0.f) rgb = rgb + mk(a[3], a[4], a[5]);
-    }
-    tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z;
-  }
+  if (threadIdx.x < pixels) { tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z; }
 }
 
 }  // namespace rt
