@@ -93,7 +93,7 @@ typedef struct b200rt_trace_params {
                                 * near-first traversal (same arithmetic and results as 2; 38 ms vs 54 ms per 32-spp chunk
                                 * of the bench workload) */
   uint32_t scene_residency;    /* 0 = auto, 1 = BVH staged in shared memory, 2 = global/L2-resident */
-  uint32_t samples_per_chunk;  /* path-trace+NIF: samples per wavefront chunk; 0 = auto */
+  uint32_t samples_per_chunk;  /* path-trace: samples per chunk of the wavefront / NIF pipeline; 0 = auto (~64 M paths per chunk) */
   uint32_t count_visits;       /* 1 = also count node visits / primitive tests (slower; parity tests) */
   uint32_t primary_pass;       /* path-trace, traversal 1/2: 0 = auto (off), 1 = on, 2 = off. On: the camera rays of a chunk
                                 * are traced by a separate warp-coherent kernel (27.5 of 32 lanes active) and the path
