@@ -354,7 +354,8 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
       const bool primB = primaryPass && sc.dev.triNormals != nullptr;
       const size_t perSlot = (slots ? (3 + 5 + 3 + 1) * sizeof(float) : 0) + (wavefront ? 120 : 0) +
                              (primaryPass ? (primB ? 32 : 16) : 0);
-      const size_t budget = wavefront ? (size_t)20 << 30 : (size_t)8 << 30;
+      static const size_t envBudget = [] { const char* e = std::getenv("B200RT_CHUNK_GIB"); return e ? (size_t)std::atoi(e) : (size_t)0; }();
+      const size_t budget = envBudget ? envBudget << 30 : (wavefront ? (size_t)20 << 30 : (size_t)8 << 30);
       while (chunk > 1 && (size_t)chunk * n * perSlot > budget) chunk /= 2;
       if (chunk > count) chunk = count ? count : 1;
       if ((size_t)chunk * n > 0xFFFFFFF0ull) return fail(B200RT_ERR_UNSUPPORTED, "ray stream too long for one chunk");
