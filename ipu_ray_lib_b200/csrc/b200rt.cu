@@ -418,8 +418,12 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
           const int wfBlock = envWfThreads > 0 ? std::min(envWfThreads, 1024) : (L.shared ? 1024 : L.block);
           const int wfGrid = L.shared ? L.grid : sc.numSMs * (1024 / L.block);
           CU_TRY(cudaMemsetAsync(sc.wfCounts.p, 0, 16, sc.stream));
+          static const bool envPhase = std::getenv("B200RT_WF_PHASE_STATS") != nullptr;
+          unsigned long long* dPhase = nullptr;
+          if (envPhase && L.count) { cudaMalloc(&dPhase, 16 * 6 * 8); cudaMemsetAsync(dPhase, 0, 16 * 6 * 8, sc.stream); }
           for (uint32_t b = 0; b < sc.desc.max_path_length; ++b) {
             w.qIn = (int)(b & 1u);
+            w.phaseStats = dPhase ? dPhase + 6 * std::min<uint32_t>(b, 15u) : nullptr;
             CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + 2, 0, 4, sc.stream));            // fetch cursor
             CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + (w.qIn ^ 1), 0, 4, sc.stream));  // next queue size
             const bool first = b == 0;  // bounce 0: camera rays are generated in the kernels, the queue is the identity
@@ -451,6 +455,18 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
             timer.end(sc.stream);
             CU_TRY(cudaGetLastError());
             launches += 2;
+          }
+          if (dPhase) {  // debugging aid (B200RT_WF_PHASE_STATS + count_visits): scheduler statistics per bounce
+            unsigned long long h[16 * 6];
+            cudaStreamSynchronize(sc.stream);
+            cudaMemcpy(h, dPhase, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaFree(dPhase);
+            for (int b = 0; b < 6; ++b) {
+              const unsigned long long* r = h + 6 * b;
+              std::fprintf(stderr, "[wf phase stats] bounce %d: trav %llu iters x %.1f lanes, leaf %llu x %.1f, fetch %llu x %.1f\n", b,
+                           r[0], r[0] ? (double)r[1] / r[0] : 0.0, r[2], r[2] ? (double)r[3] / r[2] : 0.0, r[4],
+                           r[4] ? (double)r[5] / r[4] : 0.0);
+            }
           }
         }
         if (sc.nif) {

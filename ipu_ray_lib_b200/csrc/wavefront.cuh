@@ -46,6 +46,7 @@ struct WfArgs {
   int qIn;            // queue index read by this launch
   int travThreshold;
   int writeRgbDirect; // unused (rgb is always accumulated by accumulate_kernel)
+  unsigned long long* phaseStats;  // optional [bounce][3][2]: warp iterations and participating lanes per phase (count builds)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   // instead of one per fetch step (a fetch step serves ~4 lanes)
   constexpr uint32_t kClaim = 128;
   uint32_t wNext = 0, wEnd = 0;  // warp-uniform: the unclaimed part of this warp's current batch
+  unsigned phaseIters[3] = {0u, 0u, 0u}, phaseLanes[3] = {0u, 0u, 0u};  // kCount builds: scheduler statistics
 
   auto pop_next = [&]() {
     bool found = false;
@@ -120,6 +122,11 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
     else if (cL >= cF) pick = WF_LEAF;
     else pick = WF_FETCH;
 
+    if (kCount && a.phaseStats && lane == 0) {
+      const int k = pick == WF_TRAV ? 0 : (pick == WF_LEAF ? 1 : 2);
+      phaseIters[k] += 1u;
+      phaseLanes[k] += (unsigned)(pick == WF_TRAV ? cT : (pick == WF_LEAF ? cL : cF));
+    }
     if (pick == WF_TRAV) {
       if (phase == WF_TRAV) {
         const uint32_t c0 = cur + 1, c1 = meta;
@@ -209,6 +216,8 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
       }
     }
   }
+  if (kCount && a.phaseStats && lane == 0)
+    for (int k = 0; k < 3; ++k) { atomicAdd(a.phaseStats + 2 * k, (unsigned long long)phaseIters[k]); atomicAdd(a.phaseStats + 2 * k + 1, (unsigned long long)phaseLanes[k]); }
   flush_counters(a.t.counters, nClosest, 0u, cnt, 0u, 0u);
 }
 
