@@ -17,13 +17,13 @@ PKG   := ipu_ray_lib_b200
 CSRC  := $(PKG)/csrc
 HOST  := $(PKG)/host
 
-all: $(PKG)/libb200rt.so $(PKG)/libb200rt_scene.so $(PKG)/trace oracle
+all: $(PKG)/libb200rt.so $(PKG)/libb200rt_scene.so $(PKG)/trace oracle tests/libhostpair.so
 
-$(CSRC)/b200rt.o: $(CSRC)/b200rt.cu $(CSRC)/trace_kernels.cuh $(CSRC)/path_trace_sm.cuh $(CSRC)/wavefront.cuh $(CSRC)/rt_device.cuh $(CSRC)/rt_math.h \
+$(CSRC)/b200rt.o: $(CSRC)/b200rt.cu $(CSRC)/trace_kernels.cuh $(CSRC)/wavefront.cuh $(CSRC)/rt_device.cuh $(CSRC)/rt_prims.h $(CSRC)/pair_build.hpp $(CSRC)/scene_tables.hpp $(CSRC)/rt_math.h \
                   $(CSRC)/sin_deg_table.inc $(CSRC)/nif.cuh include/b200rt.h
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(CSRC)/nif.o: $(CSRC)/nif.cu $(CSRC)/nif.cuh $(CSRC)/nif_tc.cuh $(CSRC)/nif_tc_pair.cuh $(CSRC)/nif_tc_pair2.cuh include/b200rt.h
+$(CSRC)/nif.o: $(CSRC)/nif.cu $(CSRC)/nif.cuh $(CSRC)/nif_tc.cuh include/b200rt.h
 	$(NVCC) $(NVFLAGS_NIF) -c -o $@ $<
 
 $(PKG)/libb200rt.so: $(CSRC)/b200rt.o $(CSRC)/nif.o
@@ -41,6 +41,11 @@ $(PKG)/trace: $(HOST)/trace_main.cpp $(HOST)/B200Scene.hpp $(PKG)/libb200rt.so $
 
 oracle:
 	$(MAKE) -C oracle all
+
+# test infrastructure: the traversal core of the kernels (csrc/rt_prims.h) compiled for the host, checked against the oracle
+tests/libhostpair.so: tests/host_pair_check.cpp $(CSRC)/rt_prims.h $(CSRC)/pair_build.hpp $(CSRC)/scene_tables.hpp $(CSRC)/rt_math.h \
+                      $(CSRC)/sin_deg_table.inc include/b200rt.h
+	$(CXX) $(HOSTFLAGS) -I/usr/local/cuda/include -shared -o $@ $<
 
 sass: $(PKG)/libb200rt.so
 	/usr/local/cuda/bin/cuobjdump -sass $(PKG)/libb200rt.so > /tmp/b200rt.sass

@@ -87,11 +87,11 @@ typedef struct b200rt_trace_params {
   uint32_t traversal;          /* 0 = auto (path-trace renders: 4; shadow-trace renders: 2; bare queries: 1), 1 = reference-order DFS (identical visiting
                                 * order, identical answers for ANY ray), 2 = near-first ordered DFS (same answers for
                                 * unit-length directions, which is all a render produces; ties go to the lowest leaf
-                                * index like the reference's pre-order walk), 3 = near-first DFS with the path tracer
-                                * run as a warp-scheduled state machine (same arithmetic as 2; measured slower, kept selectable),
+                                * index like the reference's pre-order walk), 3 = alias of 4 (round 1's state-machine
+                                * megakernel, measured slower, was removed),
                                 * 4 = wavefront path tracer: per-bounce trace / shade kernels over path queues in HBM with
-                                * near-first traversal (same arithmetic and results as 2; 38 ms vs 54 ms per 32-spp chunk
-                                * of the bench workload) */
+                                * near-first traversal over the derived two-children ("pair") node table (same arithmetic
+                                * and results as 2) */
   uint32_t scene_residency;    /* 0 = auto, 1 = BVH staged in shared memory, 2 = global/L2-resident */
   uint32_t samples_per_chunk;  /* path-trace: samples per chunk of the wavefront / NIF pipeline; 0 = auto (~64 M paths per chunk) */
   uint32_t count_visits;       /* 1 = also count node visits / primitive tests (slower; parity tests) */
@@ -177,8 +177,9 @@ int b200rt_nif_eval(b200rt_scene* scene, const float* uv, size_t n, float* bgr_o
 int b200rt_trace(b200rt_scene* scene, const b200rt_trace_params* params,
                  void* rays, size_t n, b200rt_ray_cb cb, void* user);
 /* Same, with TraceResult[n] already resident in DEVICE memory of the scene's device.
- * `stream` is a cudaStream_t (NULL = the scene's own stream). Returns after enqueueing
- * and synchronising the stream. */
+ * `stream` is a cudaStream_t; every kernel is enqueued on it, so the render is ordered after the
+ * caller's earlier work on that stream (NULL = the legacy default stream, which is also what a
+ * framework's "default stream" handle of 0 denotes). Returns after synchronising the stream. */
 int b200rt_trace_device(b200rt_scene* scene, const b200rt_trace_params* params,
                         void* d_rays, size_t n, void* stream);
 

@@ -17,7 +17,7 @@
 
 #include "../../include/b200rt.h"
 #include "nif.cuh"
-#include "path_trace_sm.cuh"
+#include "scene_tables.hpp"
 #include "trace_kernels.cuh"
 #include "wavefront.cuh"
 
@@ -70,10 +70,6 @@ struct DeviceBuffer {
   }
 };
 
-// Host mirrors of the reference records (layouts asserted in host/rt_types.hpp).
-struct GeomRefH { uint16_t index; uint8_t type; uint8_t pad; };
-struct MeshInfoH { uint32_t firstIndex, firstVertex, numTriangles, numVertices; };
-
 }  // namespace
 
 struct b200rt_scene {
@@ -84,8 +80,8 @@ struct b200rt_scene {
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   b200rt_scene_desc desc{};  // scalars only are used after creation
   rt::DevScene dev{};
-  uint32_t nodeBytes = 0;
-  DeviceBuffer nodes, geoms, triVerts, triNormals, spheres, discs, matIDs, materials;
+  uint32_t nodeBytes = 0, pairBytes = 0;
+  DeviceBuffer nodes, pairs, leafOrig, geoms, triVerts, triNormals, spheres, discs, matIDs, materials;
   DeviceBuffer workCounter, counters, primA, primB;
   DeviceBuffer rays;                                   // device copy of the stream (host-buffer entry point)
   DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
@@ -98,7 +94,7 @@ struct b200rt_scene {
   ~b200rt_scene() {
     cudaSetDevice(device);
     if (nif) rt::nif_destroy(nif);
-    for (DeviceBuffer* b : {&nodes, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
+    for (DeviceBuffer* b : {&nodes, &pairs, &leafOrig, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
                             &workCounter, &counters, &primA, &primB, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
                             &escapeCount, &wfRayO, &wfRayD, &wfNrm, &wfThr, &wfRng, &wfHitA, &wfHitB, &wfQ0, &wfQ1,
                             &wfCounts})
@@ -119,8 +115,6 @@ int validate_desc(const b200rt_scene_desc& d) {
   if (d.num_materials == 0 || !d.materials) return fail(B200RT_ERR_INVALID_ARG, "scene has no materials");
   if (d.num_normals != 0 && d.num_normals != d.num_verts)
     return fail(B200RT_ERR_INVALID_ARG, "mesh_normals must be empty or one per vertex");
-  if (d.max_leaf_depth > (uint32_t)rt::kMaxStack)
-    return fail(B200RT_ERR_UNSUPPORTED, "BVH deeper than 64 levels");
   if (d.path_trace && d.max_path_length == 0)
     return fail(B200RT_ERR_INVALID_ARG, "max_path_length must be at least 1 for path tracing");
   const auto* mat = (const uint32_t*)d.mat_ids;
@@ -164,22 +158,6 @@ cudaError_t dispatch_path(bool count, bool nif, const rt::TraceArgs& a, int g, i
              : launch_path<kShared, kOrdered, false, false>(a, g, b, s, st);
 }
 
-template <bool kShared, bool kCount, bool kNif>
-cudaError_t launch_path_sm(const rt::TraceArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
-  auto k = rt::path_trace_sm_kernel<kShared, kCount, kNif>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  k<<<grid, block, smem, st>>>(a);
-  return cudaGetLastError();
-}
-template <bool kShared>
-cudaError_t dispatch_path_sm(bool count, bool nif, const rt::TraceArgs& a, int g, int b, size_t s, cudaStream_t st) {
-  if (count) return nif ? launch_path_sm<kShared, true, true>(a, g, b, s, st) : launch_path_sm<kShared, true, false>(a, g, b, s, st);
-  return nif ? launch_path_sm<kShared, false, true>(a, g, b, s, st) : launch_path_sm<kShared, false, false>(a, g, b, s, st);
-}
-
 template <bool kShared, bool kOrdered, bool kCount>
 cudaError_t launch_primary(const rt::TraceArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
   auto k = rt::primary_hit_kernel<kShared, kOrdered, kCount>;
@@ -197,24 +175,27 @@ cudaError_t dispatch_primary(bool count, const rt::TraceArgs& a, int g, int b, s
 }
 
 struct LaunchPlan {
-  bool shared, ordered, count, stateMachine;
+  bool shared, ordered, count;
   int grid, block;
   size_t smem;
 };
 
-LaunchPlan plan_launch(const b200rt_scene& sc, const b200rt_trace_params& p) {
+LaunchPlan plan_launch(const b200rt_scene& sc, const b200rt_trace_params& p, bool wavefront) {
   LaunchPlan L;
   L.ordered = p.traversal != 1;  // auto = near-first
-  L.stateMachine = p.traversal == 3;  // path tracer as a warp-scheduled state machine (measured slower; kept selectable)
-  const size_t need = ((size_t)sc.nodeBytes + 15) / 16 * 16;
+  // what the kernel keeps in shared memory: the pair table (streaming kernels: shadow trace near-first, wf_trace) or
+  // the caller's own node array (reference-order walk, megakernel)
+  const bool pairTable = L.ordered && (!sc.desc.path_trace || wavefront);
+  const size_t need = (((size_t)(pairTable ? sc.pairBytes : sc.nodeBytes) + 15) / 16 * 16) + 16;
   const bool fits = need + 1024 <= (size_t)sc.maxSmemOptin;
   L.shared = p.scene_residency == 1 ? fits : (p.scene_residency == 2 ? false : fits);
   L.count = p.count_visits != 0;
   static const int envThreads = [] { const char* e = std::getenv("B200RT_THREADS_PER_SM"); return e ? std::atoi(e) : 0; }();
   // 768 threads/SM (24 warps at ~80 registers): measured 20 % faster than 512 on the path tracer
-  const int threadsPerSM = envThreads > 0 ? envThreads : 768;
+  // the megakernels and the shadow kernel are compiled with __launch_bounds__(768)
+  const int threadsPerSM = envThreads > 0 ? std::min(std::max(envThreads, 128) / 128 * 128, 768) : 768;
   if (L.shared) {
-    L.block = threadsPerSM > 1024 ? 1024 : threadsPerSM;  // one CTA per SM owns the staged BVH
+    L.block = threadsPerSM;  // one CTA per SM owns the staged BVH
     L.grid = sc.numSMs;
     L.smem = need;
   } else {
@@ -238,9 +219,6 @@ cudaError_t run_primary(b200rt_scene& sc, const LaunchPlan& L, const rt::TraceAr
                    : dispatch_primary<false, false>(L.count, a, L.grid, L.block, L.smem, sc.stream);
 }
 cudaError_t run_path(b200rt_scene& sc, const LaunchPlan& L, bool nif, const rt::TraceArgs& a) {
-  if (L.stateMachine)
-    return L.shared ? dispatch_path_sm<true>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream)
-                    : dispatch_path_sm<false>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream);
   if (L.shared) return L.ordered ? dispatch_path<true, true>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream)
                                  : dispatch_path<true, false>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream);
   return L.ordered ? dispatch_path<false, true>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream)
@@ -289,7 +267,11 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
   if (stream) sc.stream = stream;
   struct Restore { b200rt_scene& s; cudaStream_t v; ~Restore() { s.stream = v; } } restore{sc, saved};
 
-  const LaunchPlan L = plan_launch(sc, p);
+  // auto = wavefront (measured 30 % faster than the megakernel); its packed record holds the bounce in 8 bits.
+  // traversal 3 (the state-machine megakernel of round 1, measured slower) is gone: it selects the wavefront tracer too.
+  const bool wavefront = sc.desc.path_trace && (p.traversal == 4 || p.traversal == 3 ||
+                                               (p.traversal == 0 && sc.desc.max_path_length <= 255));
+  const LaunchPlan L = plan_launch(sc, p, wavefront);
   rt::TraceArgs a{};
   a.scene = sc.dev;
   a.rays = d_rays;
@@ -297,8 +279,6 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
   a.workCounter = (uint32_t*)sc.workCounter.p;
   a.counters = (rt::DeviceCounters*)sc.counters.p;
   a.nodeBytes = sc.nodeBytes;
-  static const int envThr = [] { const char* e = std::getenv("B200RT_TRAV_THRESHOLD"); return e ? std::atoi(e) : 14; }();
-  a.travThreshold = envThr;
   CU_TRY(cudaMemsetAsync(sc.counters.p, 0, sizeof(rt::DeviceCounters), sc.stream));
   CU_TRY(cudaEventRecord(sc.evStart, sc.stream));
   uint64_t launches = 0;
@@ -327,11 +307,9 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
     a.rngKey = rt::splitmix64(sc.desc.rng_seed);
     const uint32_t first = p.first_sample;
     const uint32_t count = p.num_samples ? p.num_samples : sc.desc.samples_per_pixel;
-    // auto = wavefront (measured 30 % faster than the megakernel); its packed record holds the bounce in 8 bits
-    const bool wavefront = p.traversal == 4 || (p.traversal == 0 && sc.desc.max_path_length <= 255);
     static const int envPrimary = [] { const char* e = std::getenv("B200RT_PRIMARY_PASS"); return e ? std::atoi(e) : 0; }();
     const uint32_t primarySel = p.primary_pass ? p.primary_pass : (uint32_t)envPrimary;  // 0 = auto (off: no measured gain)
-    const bool primaryPass = !wavefront && !L.stateMachine && primarySel == 1;
+    const bool primaryPass = !wavefront && primarySel == 1;
     if (!sc.nif && !wavefront && !primaryPass) {
       a.firstSample = first;
       a.endSample = first + count;
@@ -394,7 +372,7 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
         w.b.counts = (uint32_t*)sc.wfCounts.p;
         w.lastSample = first + count - 1;
         static const int envWf = [] { const char* e = std::getenv("B200RT_WF_THRESHOLD"); return e ? std::atoi(e) : 8; }();
-        w.travThreshold = envWf;
+        w.travThreshold = std::max(envWf, 1);
       }
       for (uint32_t s0 = first; s0 < first + count; s0 += chunk) {
         const uint32_t c = std::min(chunk, first + count - s0);
@@ -555,52 +533,22 @@ int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
   CU_TRY(cudaEventCreate(&sc->evStart));
   CU_TRY(cudaEventCreate(&sc->evStop));
 
+  // --- derived host tables (geometry lookup, gathered triangles, pair table) + structural validation of the BVH ---
+  rt::SceneTables tables;
+  {
+    const std::string why = rt::build_scene_tables(*d, tables);
+    if (!why.empty())
+      return fail(why.find("deeper") != std::string::npos ? B200RT_ERR_UNSUPPORTED : B200RT_ERR_INVALID_ARG, why);
+  }
   // --- node array: uploaded unchanged ---
   sc->nodeBytes = d->num_bvh_nodes * 24u;
   CU_TRY(sc->nodes.upload(d->bvh_nodes, sc->nodeBytes));
-
-  // --- geomID -> (type, first) table and gathered triangle vertices ---
-  const auto* geom = (const GeomRefH*)d->geometry;
-  const auto* info = (const MeshInfoH*)d->mesh_info;
-  const auto* tris = (const uint16_t*)d->mesh_tris;
-  const auto* verts = (const float*)d->mesh_verts;
-  const auto* normals = (const float*)d->mesh_normals;
-  std::vector<rt::GeomEntry> geoms(d->num_geometry);
-  for (uint32_t g = 0; g < d->num_geometry; ++g) {
-    geoms[g].type = geom[g].type;
-    if (geom[g].type == 0) {
-      if (geom[g].index >= d->num_meshes) return fail(B200RT_ERR_INVALID_ARG, "GeomRef mesh index out of range");
-      geoms[g].first = info[geom[g].index].firstIndex;
-    } else if (geom[g].type == 1) {
-      if (geom[g].index >= d->num_spheres) return fail(B200RT_ERR_INVALID_ARG, "GeomRef sphere index out of range");
-      geoms[g].first = geom[g].index;
-    } else if (geom[g].type == 2) {
-      if (geom[g].index >= d->num_discs) return fail(B200RT_ERR_INVALID_ARG, "GeomRef disc index out of range");
-      geoms[g].first = geom[g].index;
-    } else {
-      return fail(B200RT_ERR_INVALID_ARG, "unknown GeomType");
-    }
-  }
-  std::vector<float> tv((size_t)d->num_tris * 12, 0.f), tn;
-  if (d->num_normals) tn.assign((size_t)d->num_tris * 12, 0.f);
-  for (uint32_t m = 0; m < d->num_meshes; ++m) {
-    const MeshInfoH& mi = info[m];
-    if ((uint64_t)mi.firstIndex + mi.numTriangles > d->num_tris || (uint64_t)mi.firstVertex + mi.numVertices > d->num_verts)
-      return fail(B200RT_ERR_INVALID_ARG, "MeshInfo range exceeds the unified arrays");
-    for (uint32_t t = 0; t < mi.numTriangles; ++t) {
-      const size_t gt = (size_t)mi.firstIndex + t;
-      for (int k = 0; k < 3; ++k) {
-        const uint32_t vi = tris[3 * gt + k];
-        if (vi >= mi.numVertices) return fail(B200RT_ERR_INVALID_ARG, "triangle index exceeds its mesh's vertex window");
-        const size_t gv = (size_t)mi.firstVertex + vi;
-        std::memcpy(&tv[12 * gt + 4 * k], verts + 3 * gv, 12);
-        if (d->num_normals) std::memcpy(&tn[12 * gt + 4 * k], normals + 3 * gv, 12);
-      }
-    }
-  }
-  CU_TRY(sc->geoms.upload(geoms.data(), geoms.size() * sizeof(rt::GeomEntry)));
-  CU_TRY(sc->triVerts.upload(tv.data(), tv.size() * sizeof(float)));
-  if (d->num_normals) CU_TRY(sc->triNormals.upload(tn.data(), tn.size() * sizeof(float)));
+  sc->pairBytes = tables.pairs.numPairs * 48u;
+  CU_TRY(sc->pairs.upload(tables.pairs.words.data(), sc->pairBytes));
+  CU_TRY(sc->leafOrig.upload(tables.pairs.leafOrig.data(), tables.pairs.leafOrig.size() * 4));
+  CU_TRY(sc->geoms.upload(tables.geoms.data(), tables.geoms.size() * sizeof(rt::GeomEntry)));
+  CU_TRY(sc->triVerts.upload(tables.triVerts.data(), tables.triVerts.size() * sizeof(float)));
+  if (d->num_normals) CU_TRY(sc->triNormals.upload(tables.triNormals.data(), tables.triNormals.size() * sizeof(float)));
   CU_TRY(sc->spheres.upload(d->spheres, (size_t)d->num_spheres * 16));
   CU_TRY(sc->discs.upload(d->discs, (size_t)d->num_discs * 28));
   CU_TRY(sc->matIDs.upload(d->mat_ids, (size_t)d->num_mat_ids * 4));
@@ -618,6 +566,12 @@ int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
   sc->dev.materials = (const float*)sc->materials.p;
   sc->dev.numNodes = d->num_bvh_nodes;
   sc->dev.numMaterials = d->num_materials;
+  sc->dev.pairs = (const uint4*)sc->pairs.p;
+  sc->dev.leafOrig = (const uint32_t*)sc->leafOrig.p;
+  sc->dev.numPairs = tables.pairs.numPairs;
+  sc->dev.rootRef = tables.pairs.rootRef;
+  sc->dev.rootGeom = tables.pairs.rootGeom;
+  sc->dev.boundsFinite = tables.pairs.boundsFinite ? 1u : 0u;
   // the scalars stay; the host pointers must not be used after creation
   sc->desc.geometry = sc->desc.mesh_info = sc->desc.mesh_tris = sc->desc.mesh_verts = sc->desc.mesh_normals = nullptr;
   sc->desc.mat_ids = nullptr; sc->desc.materials = sc->desc.bvh_nodes = nullptr;
@@ -675,7 +629,9 @@ int b200rt_trace_device(b200rt_scene* sc, const b200rt_trace_params* params, voi
   if (params) p = *params;
   sc->stats = b200rt_trace_stats{};
   const auto t0 = std::chrono::steady_clock::now();
-  const int rc = render_device(*sc, p, (float*)dRays, n, (cudaStream_t)stream);
+  // NULL is the legacy default stream (what a torch "current stream" handle of 0 means), NOT the scene's private
+  // non-blocking stream: the render is ordered after the caller's earlier work on that stream.
+  const int rc = render_device(*sc, p, (float*)dRays, n, stream ? (cudaStream_t)stream : cudaStreamLegacy);
   sc->stats.trace_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return rc;
 }

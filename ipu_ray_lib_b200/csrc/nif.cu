@@ -22,7 +22,7 @@
 #include <string>
 #include <vector>
 
-#include "nif_tc_pair2.cuh"
+#include "nif_tc.cuh"
 
 namespace rt {
 
@@ -58,10 +58,7 @@ struct NifModel {
   // tensor-core path
   bool tcOk = false;
   tc::Params tc{};
-  tc::Params tc2{};   // tiling of the overlapped CTA-pair kernel (nif_tc_pair2.cuh): 128 / 192 column split
-  bool tc2Ok = false;
-  size_t pair2Smem = 0;
-  size_t tcSmem = 0, pairSmem = 0;
+  size_t tcSmem = 0;
   std::string tcWhyNot;
 };
 
@@ -153,119 +150,10 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
     m->allocs.push_back(dw);
     cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice);
     o.wimg = (const __half*)dw;
-    // CTA-pair images: the same blocks with only the columns [r n/2, (r + 1) n/2) of each, for r = 0, 1
-    {
-      std::vector<__half> pair;
-      for (int r = 0; r < 2; ++r) {
-        img.clear();
-        block(loK, r * (o.n0 / 2), o.n0 / 2, loValue);
-        if (o.n1) block(loK, o.n0 + r * (o.n1 / 2), o.n1 / 2, loValue);
-        if (hiAct) block(hiAct, r * (o.n0 / 2), o.n0 / 2, hiValue);
-        if (hiAct && o.n1) block(hiAct, o.n0 + r * (o.n1 / 2), o.n1 / 2, hiValue);
-        if (r == 0) o.pairRankBytes = (uint32_t)(img.size() * 2);
-        pair.insert(pair.end(), img.begin(), img.end());
-      }
-      void* dp = nullptr;
-      if (cudaMalloc(&dp, pair.size() * 2) != cudaSuccess) return no("cudaMalloc failed");
-      m->allocs.push_back(dp);
-      cudaMemcpy(dp, pair.data(), pair.size() * 2, cudaMemcpyHostToDevice);
-      o.wimgPair = (const __half*)dp;
-    }
-  }
-  m->pairSmem = (size_t)(t.actPlanes + tc::kStaticPlanesMax) * tc::kPlaneBytes + (size_t)tc::kPairStages * tc::kPairStageBytes +
-                (3 * tc::kPairStages + 4) * 8 + 16;
-  if (cudaFuncSetAttribute(tc::nif_mlp_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->pairSmem) != cudaSuccess) {
-    cudaGetLastError();
-    return no("cudaFuncSetAttribute(max dynamic shared memory, pair kernel) failed");
   }
   if (cudaFuncSetAttribute(tc::nif_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tcSmem) != cudaSuccess) {
     cudaGetLastError();
     return no("cudaFuncSetAttribute(max dynamic shared memory) failed");
-  }
-  return true;
-}
-
-// Same for the overlapped CTA-pair kernel (nif_tc_pair2.cuh): N0 = 128 / N1 = 192 columns, K_lo = the previous layer's
-// first 128 outputs (+ ones slice + encoded input), and only the per-rank half images (columns [r n/2, (r+1) n/2) of
-// every block). Requires hidden width 320.
-bool prepare_tc2(NifModel* m, const b200rt_nif_desc& d) {
-  const int E = (int)d.embedding_dimension, F = 4 * E;
-  if (F % 16 != 0 || 2 + F / 8 > tc2::kStaticPlanesMax || (int)d.num_layers > tc::kMaxLayers) return false;
-  tc::Params& t = m->tc2;
-  t = tc::Params{};
-  t.numLayers = (int)d.num_layers;
-  t.embed = E;
-  int width = F, prevN0 = 0;
-  std::vector<int> actRows(d.num_layers), featRows(d.num_layers);
-  for (uint32_t i = 0; i < d.num_layers; ++i) {
-    const b200rt_nif_layer& L = d.layers[i];
-    tc::Layer& o = t.layers[i];
-    const int K = (int)L.in_features;
-    o.N = (int)L.out_features; o.Npad = (o.N + 15) / 16 * 16; o.relu = L.relu;
-    const bool last = i + 1 == d.num_layers;
-    if (!last && o.N != tc2::kN0 + tc2::kN1) return false;
-    if (last && o.Npad > tc2::kN0) return false;
-    o.n0 = std::min(o.Npad, tc2::kN0);
-    o.n1 = o.Npad - o.n0;
-    if (i == 0) { if (K != F) return false; actRows[i] = 0; featRows[i] = F; }
-    else if (K == width + F) { actRows[i] = width; featRows[i] = F; }
-    else if (K == width) { actRows[i] = width; featRows[i] = 0; }
-    else return false;
-    o.actLoSlices = std::min(actRows[i], prevN0) / 16;
-    o.actHiSlices = actRows[i] / 16 - o.actLoSlices;
-    o.staticSlices = 1 + featRows[i] / 16;
-    width = o.N;
-    prevN0 = o.n0;
-  }
-  if (width != 3) return false;
-  t.maxv = d.max; t.mean0 = d.mean[0]; t.mean1 = d.mean[1]; t.mean2 = d.mean[2];
-  t.logToneMap = d.log_tone_map;
-  m->pair2Smem = (size_t)(tc2::kActPlanes + tc2::kStaticPlanesMax) * tc2::kPlaneBytes + (size_t)tc2::kStages * tc2::kStageBytes +
-                 (3 * tc2::kStages + 6) * 8 + 16;
-  int maxSmem = 0;
-  cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
-  if (m->pair2Smem > (size_t)maxSmem) return false;
-  for (uint32_t i = 0; i < d.num_layers; ++i) {
-    const b200rt_nif_layer& L = d.layers[i];
-    tc::Layer& o = t.layers[i];
-    const __half* src = reinterpret_cast<const __half*>(L.kernel_f16);
-    const __half* bias = reinterpret_cast<const __half*>(L.bias_f16);
-    const int loAct = 16 * o.actLoSlices, hiAct = 16 * o.actHiSlices;
-    const int loK = loAct + 16 * o.staticSlices;
-    std::vector<__half> img, pair;
-    auto block = [&](int kRows, int nBase, int nCols, auto&& value) {
-      const size_t at = img.size();
-      img.resize(at + (size_t)kRows * nCols, __float2half(0.f));
-      for (int k = 0; k < kRows; ++k)
-        for (int n = 0; n < nCols; ++n)
-          if (nBase + n < o.N) img[at + ((size_t)(k / 8) * nCols + n) * 8 + (k % 8)] = value(k, nBase + n);
-    };
-    auto loValue = [&](int k, int n) -> __half {
-      if (k < loAct) return src[(size_t)k * o.N + n];
-      if (k == loAct) return bias ? bias[n] : __float2half(0.f);
-      if (k < loAct + 16) return __float2half(0.f);
-      return src[(size_t)(actRows[i] + (k - loAct - 16)) * o.N + n];
-    };
-    auto hiValue = [&](int k, int n) -> __half { return src[(size_t)(loAct + k) * o.N + n]; };
-    for (int r = 0; r < 2; ++r) {
-      img.clear();
-      block(loK, r * (o.n0 / 2), o.n0 / 2, loValue);
-      if (o.n1) block(loK, o.n0 + r * (o.n1 / 2), o.n1 / 2, loValue);
-      if (hiAct) block(hiAct, r * (o.n0 / 2), o.n0 / 2, hiValue);
-      if (hiAct && o.n1) block(hiAct, o.n0 + r * (o.n1 / 2), o.n1 / 2, hiValue);
-      if (r == 0) o.pairRankBytes = (uint32_t)(img.size() * 2);
-      pair.insert(pair.end(), img.begin(), img.end());
-    }
-    void* dp = nullptr;
-    if (cudaMalloc(&dp, pair.size() * 2) != cudaSuccess) return false;
-    m->allocs.push_back(dp);
-    cudaMemcpy(dp, pair.data(), pair.size() * 2, cudaMemcpyHostToDevice);
-    o.wimgPair = (const __half*)dp;
-    o.wimg = nullptr;
-  }
-  if (cudaFuncSetAttribute(tc2::nif_mlp_tc_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->pair2Smem) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
   }
   return true;
 }
@@ -330,7 +218,6 @@ NifModel* nif_create(const b200rt_nif_desc& d, int device) {
   // Tensor-core path (the product path). Models outside its tiling rules (widths not multiples of 16)
   // run on the CUDA-core kernel below; B200RT_NIF_IMPL=simt forces that kernel for debugging.
   m->tcOk = prepare_tc(m, d);
-  m->tc2Ok = m->tcOk && prepare_tc2(m, d);
   const char* impl = std::getenv("B200RT_NIF_IMPL");
   if (impl && std::strcmp(impl, "simt") == 0) { m->tcOk = false; m->tcWhyNot = "forced by B200RT_NIF_IMPL=simt"; }
   // Weight uploads came from pageable memory on the default stream; the kernels run on the caller's non-blocking
@@ -447,46 +334,8 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
       cudaMemsetAsync(dProf, 0, (size_t)tcGrid * 16 * sizeof(unsigned long long), stream);
       params.prof = dProf;
     }
-    // CTA pairs (cta_group::2): each SM streams half of the weights. Both pair kernels are correct and parity-tested,
-    // but measured slower than the single-CTA kernel's 28 K cycles per tile and SM -- nif_tc_pair.cuh 39.6 K per 2-tile
-    // group, nif_tc_pair2.cuh (overlapped pipeline) 38.1 K -- so they are opt-in: B200RT_NIF_PAIR=1 / 2.
-    static const int pairMode = [] { const char* e = std::getenv("B200RT_NIF_PAIR"); return e ? std::atoi(e) : 0; }();
-    const bool usePair = pairMode == 1;
-    cudaError_t te;
-    if (pairMode == 2 && m->tc2Ok && sms >= 2) {  // overlapped CTA-pair kernel (nif_tc_pair2.cuh)
-      tc::Params params2 = m->tc2;
-      params2.prof = params.prof;
-      const uint32_t groups = (tcTiles + 1u) / 2u;
-      const uint32_t pairs = groups < (uint32_t)(sms / 2) ? (groups ? groups : 1u) : (uint32_t)(sms / 2);
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(2u * pairs);
-      cfg.blockDim = dim3(tc2::kThreads);
-      cfg.dynamicSmemBytes = m->pair2Smem;
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      te = cudaLaunchKernelEx(&cfg, tc2::nif_mlp_tc_pair2_kernel, params2, uvDirect, slotEscape, queue, dCount, count, out);
-    } else if (usePair && sms >= 2) {
-      const uint32_t groups = (tcTiles + 1u) / 2u;
-      const uint32_t pairs = groups < (uint32_t)(sms / 2) ? (groups ? groups : 1u) : (uint32_t)(sms / 2);
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(2u * pairs);
-      cfg.blockDim = dim3(tc::kThreads);
-      cfg.dynamicSmemBytes = m->pairSmem;
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      te = cudaLaunchKernelEx(&cfg, tc::nif_mlp_tc_pair_kernel, params, uvDirect, slotEscape, queue, dCount, count, out);
-    } else {
-      tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(params, uvDirect, slotEscape, queue, dCount, count, out);
-      te = cudaGetLastError();
-    }
+    tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(params, uvDirect, slotEscape, queue, dCount, count, out);
+    const cudaError_t te = cudaGetLastError();
     if (te != cudaSuccess) { g_nifError = cudaGetErrorString(te); return -1; }
     if (profile) {  // debugging aid: per-role cycle breakdown of CTA 0 (synchronises!)
       std::vector<unsigned long long> h((size_t)tcGrid * 16);
@@ -498,7 +347,6 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
       std::fprintf(stderr, "[nif profile] CTA0 of %u, rows %u:", tcGrid, count);
       const double tiles = h[tc::PF_TILES] ? (double)h[tc::PF_TILES] : 1.0;
       for (int i = 0; i < tc::PF_COUNT; ++i) std::fprintf(stderr, " %s=%.0f/tile", names[i], (double)h[i] / tiles);
-      std::fprintf(stderr, " wait peer weights=%.0f/tile", (double)h[tc::PF_COUNT] / tiles);
       std::fprintf(stderr, "\n");
     }
     if (launches) *launches += 1;

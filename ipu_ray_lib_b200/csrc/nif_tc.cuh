@@ -60,8 +60,6 @@ struct Layer {
   int N, Npad;          // Npad = N rounded up to 16, <= 320
   int n0, n1;           // columns of the two halves: n0 = min(Npad, 160), n1 = Npad - n0
   int relu;
-  const __half* wimgPair;     // CTA-pair kernel: rank 0's half of every block (columns [0, n/2)), then rank 1's
-  uint32_t pairRankBytes;     // bytes of one rank's image
 };
 
 struct Params {

@@ -9,34 +9,9 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
-#include "rt_math.h"
+#include "rt_prims.h"
 
 namespace rt {
-
-constexpr uint32_t kInvalidGeom = 0xFFFFu;
-constexpr uint32_t kInvalidPrim = 0xFFFFFFFFu;
-constexpr int kMaxStack = 64;  // the builder (like Embree's, bvh.hpp:52) bounds depth at 64
-
-// geomID -> what to intersect. Built on the host at scene creation from GeomRef[] + MeshInfo[]
-// (include/Scene.hpp:27-32, include/Mesh.hpp:15-20) so a leaf needs one lookup instead of two.
-struct GeomEntry {
-  uint32_t type;       // 0 mesh, 1 sphere, 2 disc
-  uint32_t first;      // mesh: global index of its first triangle; sphere/disc: index into that array
-};
-
-// Read-only scene view handed to every kernel by value.
-struct DevScene {
-  const uint2* nodes;        // CompactBVH2Node[], 24 B each, read as 3 x 8 B
-  const GeomEntry* geoms;    // [num_geometry]
-  const float4* triVerts;    // [num_tris][3]  p0,p1,p2 gathered from Triangle[] + Vec3fa[] (w unused)
-  const float4* triNormals;  // [num_tris][3]  vertex normals, or nullptr when the scene has none
-  const float4* spheres;     // {x,y,z,radius}
-  const float* discs;        // {nx,ny,nz,r,cx,cy,cz}
-  const uint32_t* matIDs;    // [num_geometry]
-  const float* materials;    // Material[], 9 words each (36 B)
-  uint32_t numNodes;
-  uint32_t numMaterials;
-};
 
 struct Hit {
   float t;          // closest t so far (starts at ray tMax)
@@ -69,143 +44,12 @@ __device__ __forceinline__ NodeWords fetch_node(const uint2* __restrict__ nodes,
   return w;
 }
 
-__device__ __forceinline__ float half_bits_to_float(uint32_t h16) {
-  return __half2float(__ushort_as_half((unsigned short)h16));
-}
-
 // CompactBVH2Node::intersect + intersectRaySlab x3 (src/CompactBVH2Node.cpp:5-22,
 // include/CompactBVH2Node.hpp:36-48). Evaluated without the per-axis early-outs: t0 only grows and
 // t1 only shrinks, so the final comparison equals the early-out result for every input incl. NaN/inf.
 // Returns the accumulated entry distance in `enter`.
 __device__ __forceinline__ bool slab_test(const NodeWords& w, V3 o, V3 inv, float tMin, float tLimit, float& enter) {
-  float t0 = tMin, t1 = tLimit;
-  {
-    const float mn = __uint_as_float(w.a.x);
-    const float mx = mn + half_bits_to_float(w.c.x & 0xffffu);
-    float tmin = (mn - o.x) * inv.x, tmax = (mx - o.x) * inv.x;
-    if (tmin > tmax) { const float s = tmin; tmin = tmax; tmax = s; }
-    tmax *= kSlabGuard;
-    t0 = tmin > t0 ? tmin : t0;
-    t1 = tmax < t1 ? tmax : t1;
-  }
-  {
-    const float mn = __uint_as_float(w.a.y);
-    const float mx = mn + half_bits_to_float(w.c.x >> 16);
-    float tmin = (mn - o.y) * inv.y, tmax = (mx - o.y) * inv.y;
-    if (tmin > tmax) { const float s = tmin; tmin = tmax; tmax = s; }
-    tmax *= kSlabGuard;
-    t0 = tmin > t0 ? tmin : t0;
-    t1 = tmax < t1 ? tmax : t1;
-  }
-  {
-    const float mn = __uint_as_float(w.b.x);
-    const float mx = mn + half_bits_to_float(w.c.y & 0xffffu);
-    float tmin = (mn - o.z) * inv.z, tmax = (mx - o.z) * inv.z;
-    if (tmin > tmax) { const float s = tmin; tmin = tmax; tmax = s; }
-    tmax *= kSlabGuard;
-    t0 = tmin > t0 ? tmin : t0;
-    t1 = tmax < t1 ? tmax : t1;
-  }
-  enter = t0;
-  return !(t0 > t1);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Per-ray constants of the triangle test: RayShearParams (src/Primitives.cpp:5-22). The reference
-// rebuilds them at every leaf (include/Mesh.hpp:89); they depend on the ray only, so they are hoisted.
-struct Shear {
-  int kz;            // iz; ix = (kz+1)%3, iy = (kz+2)%3
-  float sx, sy, sz;
-};
-__device__ __forceinline__ Shear make_shear(V3 d) {
-  Shear s;
-  s.kz = maxi(d);
-  const int kx = s.kz == 2 ? 0 : s.kz + 1;
-  const int ky = kx == 2 ? 0 : kx + 1;
-  const float dx = comp(d, kx), dy = comp(d, ky), dz = comp(d, s.kz);
-  s.sx = -dx / dz;
-  s.sy = -dy / dz;
-  s.sz = 1.f / dz;
-  return s;
-}
-__device__ __forceinline__ V3 permute(V3 v, int kz) {
-  // (c[ix], c[iy], c[iz]) for the cyclic permutation selected by kz
-  return kz == 0 ? mk(v.y, v.z, v.x) : (kz == 1 ? mk(v.z, v.x, v.y) : v);
-}
-
-// TriangleMesh::intersectTriangle (src/Mesh.cpp:6-104) with tFar = +inf, the only value the callers
-// use (include/Mesh.hpp:90-92), and ALLOW_DOUBLE_FALLBACK off (CMakeLists.txt:13). Returns t (0 = miss).
-__device__ __forceinline__ float tri_test(V3 p0, V3 p1, V3 p2, V3 o, const Shear& sh, float& b0, float& b1, float& b2) {
-  V3 p0t = permute(p0 - o, sh.kz);
-  V3 p1t = permute(p1 - o, sh.kz);
-  V3 p2t = permute(p2 - o, sh.kz);
-  p0t.x += sh.sx * p0t.z; p0t.y += sh.sy * p0t.z;
-  p1t.x += sh.sx * p1t.z; p1t.y += sh.sy * p1t.z;
-  p2t.x += sh.sx * p2t.z; p2t.y += sh.sy * p2t.z;
-  const float e0 = p1t.x * p2t.y - p1t.y * p2t.x;
-  const float e1 = p2t.x * p0t.y - p2t.y * p0t.x;
-  const float e2 = p0t.x * p1t.y - p0t.y * p1t.x;
-  if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return 0.f;
-  const float det = e0 + e1 + e2;
-  if (det == 0) return 0.f;
-  p0t.z *= sh.sz; p1t.z *= sh.sz; p2t.z *= sh.sz;
-  const float tScaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
-  const float inf = __int_as_float(0x7f800000);
-  if (det < 0.f && (tScaled >= 0.f || tScaled < inf * det)) return 0.f;
-  else if (det > 0.f && (tScaled <= 0.f || tScaled > inf * det)) return 0.f;
-  const float invDet = 1 / det;
-  b0 = e0 * invDet; b1 = e1 * invDet; b2 = e2 * invDet;
-  const float t = tScaled * invDet;
-  // PBRT-style conservative error bound (Mesh.cpp:85-101); maxc() keeps the reference's chain.
-  const float maxZt = maxc(vabs(mk(p0t.z, p1t.z, p2t.z)));
-  const float deltaZ = kGamma3 * maxZt;
-  const float maxXt = maxc(vabs(mk(p0t.x, p1t.x, p2t.x)));
-  const float maxYt = maxc(vabs(mk(p0t.y, p1t.y, p2t.y)));
-  const float deltaX = kGamma5 * (maxXt + maxZt);
-  const float deltaY = kGamma5 * (maxYt + maxZt);
-  const float deltaE = 2 * (kGamma2 * maxXt * maxYt + deltaY * maxXt + deltaX * maxYt);
-  const float maxE = maxc(vabs(mk(e0, e1, e2)));
-  const float deltaT = 3 * (kGamma3 * maxE * maxZt + deltaE * maxZt + deltaZ * maxE) * fabsf(invDet);
-  if (t <= deltaT) return 0.f;
-  return t;
-}
-
-// Sphere::intersect (src/Primitives.cpp:24-46). Returns t (0 = miss).
-__device__ __forceinline__ float sphere_test(float4 s, V3 o, V3 d, float tMin) {
-  const V3 f = mk(s.x, s.y, s.z) - o;
-  const float radius2 = s.w * s.w;
-  const float rd2 = 1.f / norm2(d);
-  const float tca = dot(f, d) * rd2;
-  if (tca < 0.f) return 0.f;
-  const V3 l = f - d * tca;
-  const float l2 = norm2(l);
-  if (l2 > radius2) return 0.f;
-  const float td = sqrtf(radius2 - l2) * rd2;
-  float t0 = tca - td, t1 = tca + td;
-  if (t0 > t1) { const float s2 = t0; t0 = t1; t1 = s2; }
-  if (t0 < tMin) {
-    t0 = t1;
-    if (t0 < tMin) return 0.f;
-  }
-  return t0;
-}
-
-// Disc::intersect (src/Primitives.cpp:48-67), including its abs(c.n) plane offset. Returns t (0 = miss).
-__device__ __forceinline__ float disc_test(const float* __restrict__ p, V3 o, V3 d) {
-  const V3 n = mk(__ldg(p + 0), __ldg(p + 1), __ldg(p + 2));
-  const float r = __ldg(p + 3);
-  const V3 c = mk(__ldg(p + 4), __ldg(p + 5), __ldg(p + 6));
-  const float angle = dot(n, d);
-  if (angle != 0.f) {
-    const float dd = fabsf(dot(c, n));
-    const float t = -(dot(n, o) + dd) / angle;
-    if (t > kMachineEps) {
-      const V3 hp = o + d * t;
-      const float d2 = norm2(hp - c);
-      if (d2 < r * r) return t;
-    }
-  }
-  return 0.f;
+  return slab_exact(__uint_as_float(w.a.x), __uint_as_float(w.a.y), __uint_as_float(w.b.x), w.c.x, w.c.y, o, inv, tMin, tLimit, enter);
 }
 
 // One leaf: dispatch on the geometry type (primLookup + virtual Primitive::intersect,
@@ -390,28 +234,9 @@ __device__ __forceinline__ bool any_hit(const DevScene& sc, const uint2* __restr
 // ---------------------------------------------------------------------------------------------
 // Shading-side helpers.
 
-// Primitive::normal at the updated hit point (Render.hpp:15-23 -> Mesh.hpp:106-121 /
-// Primitives.hpp:49-51 / :73). For meshes the reference computes the normal inside intersect() for
-// every accepted candidate; it is a pure function of the winning triangle, so it is computed once here.
+// Primitive::normal at the updated hit point (see prim_normal in rt_prims.h).
 __device__ __forceinline__ V3 hit_normal(const DevScene& sc, const Hit& h, V3 hitPoint) {
-  const GeomEntry g = sc.geoms[h.geomID];
-  if (g.type == 0) {
-    if (sc.triNormals == nullptr) {
-      const float4* tv = sc.triVerts + 3u * h.tri;
-      const float4 a = __ldg(tv), b = __ldg(tv + 1), c = __ldg(tv + 2);
-      const V3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
-      return normalized(cross(p1 - p0, p2 - p0));
-    }
-    const float4* tn = sc.triNormals + 3u * h.tri;
-    const float4 a = __ldg(tn), b = __ldg(tn + 1), c = __ldg(tn + 2);
-    return normalized((mk(a.x, a.y, a.z) * h.b0 + mk(b.x, b.y, b.z) * h.b1) + mk(c.x, c.y, c.z) * h.b2);
-  }
-  if (g.type == 1) {
-    const float4 s = __ldg(sc.spheres + g.first);
-    return normalized(hitPoint - mk(s.x, s.y, s.z));
-  }
-  const float* p = sc.discs + 7u * g.first;
-  return mk(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+  return prim_normal(sc, h.geomID, h.tri, h.b0, h.b1, h.b2, hitPoint);
 }
 
 // offsetRay (Render.hpp:29-33)

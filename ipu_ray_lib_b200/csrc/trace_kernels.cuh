@@ -32,7 +32,7 @@ struct TraceArgs {
   uint32_t numRays;
   uint32_t* workCounter;    // persistent-warp chunk counter (zeroed before launch)
   DeviceCounters* counters;
-  uint32_t nodeBytes;       // size of the node array when staged into shared memory
+  uint32_t nodeBytes;       // size of the node array when staged into shared memory (reference-order / megakernel paths)
   // shadow trace
   float lightX, lightY, lightZ, ambient;
   // path trace
@@ -79,6 +79,16 @@ __device__ __forceinline__ const uint2* stage_nodes(const TraceArgs& a, uint2* s
   return smem;
 }
 
+// Same for the pair table (rt_prims.h) that the streaming kernels traverse: 48 B per inner node.
+template <bool kShared>
+__device__ __forceinline__ const uint4* stage_pairs(const TraceArgs& a, uint4* smem) {
+  if (!kShared) return a.scene.pairs;
+  const uint32_t n16 = a.scene.numPairs * 3u;
+  for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) smem[i] = __ldg(a.scene.pairs + i);
+  __syncthreads();
+  return smem;
+}
+
 template <bool kShared, bool kOrdered, bool kCount>
 __device__ __forceinline__ void closest_hit(const DevScene& sc, const uint2* nodes, V3 o, V3 d, float tMin, float tMax,
                                             Hit& h, Counters& c) {
@@ -87,13 +97,64 @@ __device__ __forceinline__ void closest_hit(const DevScene& sc, const uint2* nod
 }
 
 // -------------------------------------------------------------------------------------------------
+// traceShadowRay for one ray (include/Render.hpp:37-72): closest hit, then on a hit updateHit, the shadow ray towards
+// the light and Lambert + ambient. kOrdered = near-first over the pair table; otherwise the reference's visiting order
+// over the caller's own node array (identical node / primitive counters).
+struct ShadowOut {
+  bool hit;
+  V3 color, o, n;
+  float t;
+  uint32_t primID, geomID;
+};
+template <bool kShared, bool kOrdered, bool kCount>
+__device__ __forceinline__ ShadowOut shadow_one(const TraceArgs& a, const void* table, V3 o, V3 d, float tMin, float tMax,
+                                                Counters& cnt, unsigned& nOccl) {
+  const DevScene& sc = a.scene;
+  ShadowOut r;
+  Hit h;
+  if (kOrdered) {
+    const uint4* pairs = static_cast<const uint4*>(table);
+    uint2 stack[kMaxStack];
+    PairHit ph;
+    pair_closest_hit<kShared, kCount>(sc, pairs, o, d, tMin, tMax, ph, stack, cnt.nodeVisits, cnt.primTests);
+    h.t = ph.t; h.geomID = ph.geomID; h.b0 = ph.b0; h.b1 = ph.b1; h.b2 = ph.b2; h.node = 0;
+    hit_ids(sc, ph, h.primID, h.tri);
+  } else {
+    closest_hit_ref_order<kShared, kCount>(sc, static_cast<const uint2*>(table), o, d, tMin, tMax, h, cnt);
+  }
+  r.hit = h.geomID != kInvalidGeom;
+  r.t = h.t; r.primID = h.primID; r.geomID = h.geomID;
+  r.o = o; r.n = mk(0.f, 0.f, 1.f); r.color = mk(0.f, 0.f, 0.f);
+  if (r.hit) {
+    // updateHit (Render.hpp:15-23)
+    r.o = o + d * h.t;
+    r.n = hit_normal(sc, h, r.o);
+    const Mat m = load_material(sc, h.geomID);
+    // shadow ray towards the light (Render.hpp:50-60); tMax is the distance BEFORE the offset
+    const V3 lightOffset = mk(a.lightX, a.lightY, a.lightZ) - r.o;
+    const V3 sd = normalized(lightOffset);
+    const V3 so = offset_origin(r.o, sd, r.n);
+    const float sMax = sqrtf(norm2(lightOffset));
+    r.color = m.albedo * a.ambient;
+    nOccl++;
+    bool occluded;
+    if (kOrdered) {
+      uint32_t stack[kMaxStack];
+      occluded = pair_any_hit<kShared, kCount>(sc, static_cast<const uint4*>(table), so, sd, 0.f, sMax, stack, cnt.nodeVisits, cnt.primTests);
+    } else {
+      occluded = any_hit<kShared, kCount>(sc, static_cast<const uint2*>(table), so, sd, 0.f, sMax, cnt);
+    }
+    if (!occluded) r.color = r.color + m.albedo * dot(sd, r.n);
+  }
+  return r;
+}
+
 template <bool kShared, bool kOrdered, bool kCount>
 __global__ void __launch_bounds__(768) shadow_trace_kernel(const TraceArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  const uint2* nodes = stage_nodes<kShared>(a, reinterpret_cast<uint2*>(smemRaw));
-  const DevScene& sc = a.scene;
+  const void* table = kOrdered ? static_cast<const void*>(stage_pairs<kShared>(a, reinterpret_cast<uint4*>(smemRaw)))
+                               : static_cast<const void*>(stage_nodes<kShared>(a, reinterpret_cast<uint2*>(smemRaw)));
   const unsigned lane = threadIdx.x & 31;
-  const V3 light = mk(a.lightX, a.lightY, a.lightZ);
   Counters cnt = {0u, 0u};
   unsigned nClosest = 0, nOccl = 0;
 
@@ -106,32 +167,19 @@ __global__ void __launch_bounds__(768) shadow_trace_kernel(const TraceArgs a) {
     if (idx >= a.numRays) continue;
     float* tr = a.rays + (size_t)idx * TR_WORDS;
 
-    V3 o = mk(tr[TR_ORIGIN], tr[TR_ORIGIN + 1], tr[TR_ORIGIN + 2]);
+    const V3 o = mk(tr[TR_ORIGIN], tr[TR_ORIGIN + 1], tr[TR_ORIGIN + 2]);
     const V3 d = mk(tr[TR_DIR], tr[TR_DIR + 1], tr[TR_DIR + 2]);
     const float tMin = tr[TR_TMIN], tMax = tr[TR_TMAX];
-    Hit h;
     nClosest++;
-    closest_hit<kShared, kOrdered, kCount>(sc, nodes, o, d, tMin, tMax, h, cnt);
-    if (h.geomID != kInvalidGeom) {
-      // updateHit (Render.hpp:15-23)
-      o = o + d * h.t;
-      const V3 n = hit_normal(sc, h, o);
-      const Mat m = load_material(sc, h.geomID);
-      // shadow ray towards the light (Render.hpp:50-60); tMax is the distance BEFORE the offset
-      const V3 lightOffset = light - o;
-      const V3 sd = normalized(lightOffset);
-      const V3 so = offset_origin(o, sd, n);
-      const float sMax = sqrtf(norm2(lightOffset));
-      V3 color = m.albedo * a.ambient;
-      nOccl++;
-      if (!any_hit<kShared, kCount>(sc, nodes, so, sd, 0.f, sMax, cnt)) color = color + m.albedo * dot(sd, n);
-      tr[TR_RGB] = color.x; tr[TR_RGB + 1] = color.y; tr[TR_RGB + 2] = color.z;
-      tr[TR_ORIGIN] = o.x; tr[TR_ORIGIN + 1] = o.y; tr[TR_ORIGIN + 2] = o.z;
-      tr[TR_TMAX] = h.t;
-      tr[TR_PRIM] = __uint_as_float(h.primID);
-      tr[TR_NORMAL] = n.x; tr[TR_NORMAL + 1] = n.y; tr[TR_NORMAL + 2] = n.z;
+    const ShadowOut r = shadow_one<kShared, kOrdered, kCount>(a, table, o, d, tMin, tMax, cnt, nOccl);
+    if (r.hit) {
+      tr[TR_RGB] = r.color.x; tr[TR_RGB + 1] = r.color.y; tr[TR_RGB + 2] = r.color.z;
+      tr[TR_ORIGIN] = r.o.x; tr[TR_ORIGIN + 1] = r.o.y; tr[TR_ORIGIN + 2] = r.o.z;
+      tr[TR_TMAX] = r.t;
+      tr[TR_PRIM] = __uint_as_float(r.primID);
+      tr[TR_NORMAL] = r.n.x; tr[TR_NORMAL + 1] = r.n.y; tr[TR_NORMAL + 2] = r.n.z;
       const uint32_t ids = __float_as_uint(tr[TR_IDS]);
-      tr[TR_IDS] = __uint_as_float((ids & 0xffff0000u) | h.geomID);
+      tr[TR_IDS] = __uint_as_float((ids & 0xffff0000u) | r.geomID);
     } else {
       const uint32_t ids = __float_as_uint(tr[TR_IDS]);
       tr[TR_IDS] = __uint_as_float(ids | (kFlagEscaped << 16));
@@ -363,27 +411,6 @@ __global__ void __launch_bounds__(768) path_trace_kernel(const TraceArgs a) {
   flush_counters(a.counters, nClosest, 0u, cnt, nSamples, nEscaped);
 }
 
-// rgb += color_s; rgb += throughput_s * (bgr[2], bgr[1], bgr[0]) for s in chunk order
-// (PathTrace `result.rgb += color` followed by PostProcessEscapedRays, codelets/TraceCodelets.cpp:257, :361-382).
-__global__ void accumulate_kernel(float* rays, uint32_t numRays, uint32_t chunk, const float* slotColor,
-                                  const float* slotEscape, const float* slotEnv) {
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= numRays) return;
-  float* tr = rays + (size_t)idx * TR_WORDS;
-  V3 rgb = mk(tr[TR_RGB], tr[TR_RGB + 1], tr[TR_RGB + 2]);
-  for (uint32_t c = 0; c < chunk; ++c) {
-    const size_t slot = (size_t)idx * chunk + c;
-    const float* col = slotColor + 3 * slot;
-    rgb = rgb + mk(col[0], col[1], col[2]);
-    const float* se = slotEscape + 5 * slot;
-    if (se[3] >= 0.f) {
-      const float* env = slotEnv + 3 * slot;
-      rgb = rgb + mk(se[0], se[1], se[2]) * mk(env[2], env[1], env[0]);
-    }
-  }
-  tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z;
-}
-
 // Bare-ray queries for the parity tests (b200rt_intersect / b200rt_occluded).
 struct QueryHit {
   float t;
@@ -400,7 +427,15 @@ __global__ void intersect_kernel(DevScene sc, const float* rays, uint32_t n, Que
     const V3 o = mk(r[0], r[1], r[2]), d = mk(r[4], r[5], r[6]);
     Hit h;
     nq = 1;
-    closest_hit<false, kOrdered, true>(sc, sc.nodes, o, d, r[3], r[7], h, cnt);
+    if (kOrdered) {  // near-first over the pair table, as the render kernels traverse
+      uint2 stack[kMaxStack];
+      PairHit ph;
+      pair_closest_hit<false, true>(sc, sc.pairs, o, d, r[3], r[7], ph, stack, cnt.nodeVisits, cnt.primTests);
+      h.t = ph.t; h.geomID = ph.geomID; h.b0 = ph.b0; h.b1 = ph.b1; h.b2 = ph.b2; h.node = 0;
+      hit_ids(sc, ph, h.primID, h.tri);
+    } else {
+      closest_hit_ref_order<false, true>(sc, sc.nodes, o, d, r[3], r[7], h, cnt);
+    }
     QueryHit q;
     q.t = h.t; q.geomID = h.geomID; q.primID = h.primID; q.nx = q.ny = q.nz = 0.f;
     if (h.geomID != kInvalidGeom) {

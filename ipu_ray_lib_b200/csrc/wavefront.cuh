@@ -15,7 +15,7 @@
 //                paths write their colour / escape record (and the HitRecord if they are the last sample)
 //
 // The arithmetic per path is the megakernel's, statement for statement, so results are bit-identical; only the
-// grouping of work changes. rgb is accumulated afterwards in sample order by accumulate_kernel.
+// grouping of work changes. rgb is accumulated afterwards in sample order by wf_accumulate_kernel.
 #pragma once
 #include "trace_kernels.cuh"
 
@@ -45,7 +45,6 @@ struct WfArgs {
   uint32_t lastSample;  // the sample whose HitRecord is left in the ray stream (last of the whole call)
   int qIn;            // queue index read by this launch
   int travThreshold;
-  int writeRgbDirect; // unused (rgb is always accumulated by accumulate_kernel)
   unsigned long long* phaseStats;  // optional [bounce][3][2]: warp iterations and participating lanes per phase (count builds)
 };
 
@@ -64,12 +63,22 @@ __device__ __forceinline__ void wf_camera_path(const WfArgs& a, uint32_t p, V3& 
 }
 
 // ------------------------------------------------------------------------------------------------
-enum : int { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2, WF_DONE = 3 };
+// wf_trace: one closest-hit query per path of the bounce's queue (CompactBvh::intersect, include/CompactBvh.hpp:80-139,
+// near-first order over the pair table of rt_prims.h).
+//
+// Persistent 1024-thread CTAs, the pair table staged in shared memory when it fits. Every lane owns one query at a
+// time and is in one of three phases: TRAV (it holds an inner node: load its 48-byte pair record, test both child
+// boxes, descend / defer / pop), LEAF (it holds a leaf: run the primitive test, then pop) or FETCH (its query is
+// finished: store the hit, take the next ray of the warp's batch, test the root). A warp iteration executes ONE
+// phase, chosen by ballot: inner-node steps as long as at least `travThreshold` lanes want one (a single ballot on
+// that path), otherwise whichever phase most lanes wait for. Lanes therefore never wait for a neighbour's long
+// traversal, only for their phase to be scheduled.
+enum : uint32_t { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2, WF_DONE = 3 };
 
 template <bool kShared, bool kCount, bool kFirst>
 __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  const uint2* nodes = stage_nodes<kShared>(a.t, reinterpret_cast<uint2*>(smemRaw));
+  const uint4* pairs = stage_pairs<kShared>(a.t, reinterpret_cast<uint4*>(smemRaw));
   const DevScene& sc = a.t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
   const float inf = __int_as_float(0x7f800000);
@@ -80,22 +89,26 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   Counters cnt = {0u, 0u};
   unsigned nClosest = 0;
 
+  // the lane's query
   V3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 0.f, -1.f), inv = mk(0.f, 0.f, 0.f);
   Shear sh;
   sh.kz = 2; sh.sx = sh.sy = sh.sz = 0.f;
-  Hit hit;
-  hit.t = inf; hit.geomID = kInvalidGeom; hit.primID = kInvalidPrim; hit.tri = 0; hit.node = 0;
-  hit.b0 = hit.b1 = hit.b2 = 0.f;
-  uint32_t cur = 0, meta = 0, curGeom = kInvalidGeom, path = 0xFFFFFFFFu;
-  uint2 stack[kMaxStack];
+  PairHit hit;
+  hit.t = inf; hit.geomID = kInvalidGeom; hit.ref = 0u; hit.key = 0u; hit.b0 = hit.b1 = hit.b2 = 0.f;
+  uint32_t ref = 0u;       // TRAV: pair index of the inner node held; LEAF: leaf reference held
+  uint32_t geom = 0u;      // LEAF: geomID of the leaf held
+  uint32_t key = 0u;       // LEAF: pair * 2 + side of the leaf held
+  uint32_t path = 0xFFFFFFFFu;
+  bool fast = true;        // the query may use the NaN-free slab test (fast_slab_ok)
+  uint2 stack[kMaxStack];  // deferred children: {key, entry distance}
   int sp = 0;
-  int phase = WF_FETCH;
+  uint32_t phase = WF_FETCH;
   // ray ids are claimed from the bounce's queue kClaim at a time per warp: one same-address atomic per 128 rays
-  // instead of one per fetch step (a fetch step serves ~4 lanes)
   constexpr uint32_t kClaim = 128;
   uint32_t wNext = 0, wEnd = 0;  // warp-uniform: the unclaimed part of this warp's current batch
   unsigned phaseIters[3] = {0u, 0u, 0u}, phaseLanes[3] = {0u, 0u, 0u};  // kCount builds: scheduler statistics
 
+  // next deferred child that can still hold a closer hit (the reference's pop-time slab test), or the end of the query
   auto pop_next = [&]() {
     bool found = false;
     uint2 e = make_uint2(0u, 0u);
@@ -104,51 +117,45 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
       if (!(__uint_as_float(e.y) > hit.t)) { found = true; break; }
     }
     if (!found) { phase = WF_FETCH; return; }
-    cur = e.x;
-    const uint2* p = nodes + 3u * cur;
-    if (kShared) { meta = p[1].y; curGeom = p[2].y >> 16; }
-    else { meta = __ldg(p + 1).y; curGeom = __ldg(p + 2).y >> 16; }
-    phase = curGeom != kInvalidGeom ? WF_LEAF : WF_TRAV;
+    key = e.x;
+    fetch_child_ref<kShared>(pairs, key, ref, geom);
+    phase = geom != kInvalidGeom ? WF_LEAF : WF_TRAV;
   };
 
   while (true) {
     const unsigned mT = __ballot_sync(full, phase == WF_TRAV);
-    const unsigned mL = __ballot_sync(full, phase == WF_LEAF);
-    const unsigned mF = __ballot_sync(full, phase == WF_FETCH);
-    if (!(mT | mL | mF)) break;
-    const int cT = __popc(mT), cL = __popc(mL), cF = __popc(mF);
-    int pick;
-    if (cT >= a.travThreshold || (cT >= cL && cT >= cF)) pick = WF_TRAV;
-    else if (cL >= cF) pick = WF_LEAF;
-    else pick = WF_FETCH;
-
-    if (kCount && a.phaseStats && lane == 0) {
-      const int k = pick == WF_TRAV ? 0 : (pick == WF_LEAF ? 1 : 2);
-      phaseIters[k] += 1u;
-      phaseLanes[k] += (unsigned)(pick == WF_TRAV ? cT : (pick == WF_LEAF ? cL : cF));
+    const int cT = __popc(mT);
+    uint32_t pick = WF_TRAV;
+    unsigned mF = 0u;
+    int cF = 0, cL = 0;
+    if (cT < a.travThreshold) {
+      const unsigned mL = __ballot_sync(full, phase == WF_LEAF);
+      mF = __ballot_sync(full, phase == WF_FETCH);
+      if (!(mT | mL | mF)) break;
+      cL = __popc(mL); cF = __popc(mF);
+      if (!(cT >= cL && cT >= cF)) pick = cL >= cF ? WF_LEAF : WF_FETCH;
     }
+    if (kCount && a.phaseStats && lane == 0) {
+      phaseIters[pick] += 1u;
+      phaseLanes[pick] += (unsigned)(pick == WF_TRAV ? cT : (pick == WF_LEAF ? cL : cF));
+    }
+
     if (pick == WF_TRAV) {
       if (phase == WF_TRAV) {
-        const uint32_t c0 = cur + 1, c1 = meta;
-        const NodeWords w0 = fetch_node<kShared>(nodes, c0);
-        const NodeWords w1 = fetch_node<kShared>(nodes, c1);
+        const PairWords w = fetch_pair<kShared>(pairs, ref);
         if (kCount) cnt.nodeVisits += 2;
+        bool h0, h1;
         float e0, e1;
-        const bool h0 = slab_test(w0, o, inv, 0.f, hit.t, e0);
-        const bool h1 = slab_test(w1, o, inv, 0.f, hit.t, e1);
-        if (h0 && h1) {
-          const bool firstNear = !(e1 < e0);  // ties go to the first child, like pre-order
-          stack[sp++] = make_uint2(firstNear ? c1 : c0, __float_as_uint(firstNear ? e1 : e0));
-          cur = firstNear ? c0 : c1;
-          meta = firstNear ? w0.b.y : w1.b.y;
-          curGeom = (firstNear ? w0.c.y : w1.c.y) >> 16;
-          if (curGeom != kInvalidGeom) phase = WF_LEAF;
-        } else if (h0) {
-          cur = c0; meta = w0.b.y; curGeom = w0.c.y >> 16;
-          if (curGeom != kInvalidGeom) phase = WF_LEAF;
-        } else if (h1) {
-          cur = c1; meta = w1.b.y; curGeom = w1.c.y >> 16;
-          if (curGeom != kInvalidGeom) phase = WF_LEAF;
+        if (fast) pair_slabs<true>(w, o, inv, 0.f, hit.t, h0, h1, e0, e1);
+        else pair_slabs<false>(w, o, inv, 0.f, hit.t, h0, h1, e0, e1);
+        if (h0 | h1) {
+          const bool goL = h0 && (!h1 || !(e1 < e0));  // ties go to the first child, like pre-order
+          const uint32_t k0 = ref * 2u;
+          if (h0 && h1) stack[sp++] = make_uint2(goL ? k0 + 1u : k0, __float_as_uint(goL ? e1 : e0));
+          geom = (goL ? w.q1.y : w.q2.w) >> 16;
+          key = goL ? k0 : k0 + 1u;
+          ref = goL ? w.q0.w : w.q2.y;
+          if (geom != kInvalidGeom) phase = WF_LEAF;
         } else {
           pop_next();
         }
@@ -156,10 +163,10 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
     } else if (pick == WF_LEAF) {
       if (phase == WF_LEAF) {
         if (kCount) cnt.primTests++;
-        const LeafResult r = leaf_test(sc, curGeom, meta, o, d, 0.f, sh);
-        if (r.t > 0.f && (r.t < hit.t || (r.t == hit.t && hit.geomID != kInvalidGeom && cur < hit.node))) {
-          hit.t = r.t; hit.geomID = curGeom; hit.primID = sc.geoms[curGeom].type == 0 ? meta : 0u;
-          hit.tri = r.tri; hit.node = cur; hit.b0 = r.b0; hit.b1 = r.b1; hit.b2 = r.b2;
+        float b0, b1, b2;
+        const float t = leaf_eval(sc, ref, o, d, 0.f, sh, b0, b1, b2);
+        if (accept_hit(sc, t, 0.f, hit, key)) {
+          hit.t = t; hit.geomID = geom; hit.ref = ref; hit.key = key; hit.b0 = b0; hit.b1 = b1; hit.b2 = b2;
         }
         pop_next();
       }
@@ -178,12 +185,13 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
       wNext += min((uint32_t)cF, avail);
       if (served) {
         if (path != 0xFFFFFFFFu) {
-          a.b.hitA[path] = make_float4(hit.t, __uint_as_float(hit.geomID), __uint_as_float(hit.primID), __uint_as_float(hit.tri));
+          uint32_t primID, tri;
+          hit_ids(sc, hit, primID, tri);
+          a.b.hitA[path] = make_float4(hit.t, __uint_as_float(hit.geomID), __uint_as_float(primID), __uint_as_float(tri));
           if (a.b.hitB) a.b.hitB[path] = make_float4(hit.b0, hit.b1, hit.b2, 0.f);
           path = 0xFFFFFFFFu;
         }
         if (qi >= count) {
-          path = 0xFFFFFFFFu;
           phase = WF_DONE;
         } else {
           if (kFirst) {
@@ -200,17 +208,15 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
           nClosest++;
           inv = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
           sh = make_shear(d);
-          hit.t = inf; hit.geomID = kInvalidGeom; hit.primID = kInvalidPrim; hit.tri = 0; hit.node = 0;
-          hit.b0 = hit.b1 = hit.b2 = 0.f;
+          fast = fast_slab_ok(sc, o, inv, 0.f, inf);
+          hit.t = inf; hit.geomID = kInvalidGeom; hit.ref = 0u; hit.key = 0u; hit.b0 = hit.b1 = hit.b2 = 0.f;
           sp = 0;
-          const NodeWords w = fetch_node<kShared>(nodes, 0);
           if (kCount) cnt.nodeVisits++;
-          float enter;
-          if (!slab_test(w, o, inv, 0.f, hit.t, enter)) {
-            phase = WF_FETCH;  // missed the scene: result (no hit) is stored on the next fetch step
+          if (!root_slab(sc, o, inv, 0.f, inf, fast)) {
+            phase = WF_FETCH;  // missed the scene: the result (no hit) is stored on the next fetch step
           } else {
-            cur = 0; meta = w.b.y; curGeom = w.c.y >> 16;
-            phase = curGeom != kInvalidGeom ? WF_LEAF : WF_TRAV;
+            ref = sc.rootRef; geom = sc.rootGeom; key = 0u;
+            phase = geom != kInvalidGeom ? WF_LEAF : WF_TRAV;
           }
         }
       }

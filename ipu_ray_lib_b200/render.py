@@ -106,7 +106,8 @@ class B200Scene:
         return rays
 
     def execute_device(self, device_ptr: int, num_rays: int, stream: int = 0, **params) -> None:
-        """Render a TraceResult stream already resident in HBM (e.g. a torch uint8 tensor's data_ptr)."""
+        """Render a TraceResult stream already resident in HBM (e.g. a torch uint8 tensor's data_ptr) on `stream`
+        (a cudaStream_t handle; 0 = the legacy default stream, i.e. torch's default stream)."""
         p = self.make_params(**params)
         _check(capi.lib().b200rt_trace_device(self._handle, C.byref(p), C.c_void_p(device_ptr), num_rays,
                                               C.c_void_p(stream) if stream else None))
