@@ -1,22 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the trace path (BASELINE.json: path-trace Mrays/s & samples/s, 1440^2, built-in scene).
+"""bench.py — benchmark of the trace path (BASELINE.json: path-trace Mrays/s & samples/s at 1/2/4/8 B200 vs CPU).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU kernels on the host cores
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path, BASELINE configs[1] (the headline)
+    python bench.py --config {1,2,3,4,5} ...                   # the other named configurations (1-based, see CONFIGS)
+    python bench.py --impl reference --gpus N --steps K ...     # the reference's own CPU kernels on the host cores
 
-A STEP is one complete render of the workload: configs[1] of BASELINE.json — the built-in box scene,
-path-traced with the NIF environment light at 1440x1440, 1000 spp (maxPathLength 10, roulette start 3,
-anti-alias 0.25, seed 1442; synthetic fixed-seed NIF weights because the trained ones are missing from
-the reference checkout). With N > 1 the same image is partitioned ray-data-parallel: the TraceResult
-stream is cut into the reference's ray batches (8640 rays) and batch i goes to rank i % N
-(src/IpuScene.cpp:676-684); scene/BVH/NIF weights are replicated; there is no collective on the data
-path, only the final framebuffer gather (rgb) to rank 0 over NCCL, which is inside the timed step.
+A STEP is one complete render of the workload. Default = configs[1] of BASELINE.json: the built-in box scene,
+path-traced with the NIF environment light at 1440x1440, 1000 spp (maxPathLength 10, roulette start 3, anti-alias 0.25,
+seed 1442; synthetic fixed-seed NIF weights because the trained ones are missing from the reference checkout).
+With N > 1 the same image is partitioned ray-data-parallel: the TraceResult stream is cut into the reference's ray
+batches (8640 rays) and batch i goes to rank i % N (src/IpuScene.cpp:676-684); scene/BVH/NIF weights are replicated;
+there is no collective on the data path, only the final framebuffer gather (rgb) to rank 0 over NCCL, inside the step.
 
 Numbers on the JSON line:
   value   Mrays/s = BVH queries actually issued (closest-hit + occlusion, counted on the device) / s,
           rays already resident in HBM, device-timed with CUDA events on the launching stream, max over ranks.
-  e2e     same metric through the public C-ABI call with HOST buffers: every step copies its shard of
-          the ray stream host->device, renders, copies it back (b200rt_trace).
+  e2e     same metric through the public C-ABI call with HOST buffers: every step streams its shard of the ray stream
+          host->device, renders, streams it back (b200rt_trace: tiles pipelined over three CUDA streams).
   samples_per_s  pixels * spp / s for the same timed region.
   roofline / roofline_kernels, cpu_baseline, clocks: see DESIGN.md "Measurement".
 """
@@ -45,37 +45,91 @@ METRIC = "path_trace_mrays_per_s"
 UNIT = "Mrays/s"
 RAYS_PER_BATCH = 8640
 
+# BASELINE.json `configs`, 1-based. (steps, warmup) are the defaults when the command line gives none.
+CONFIGS = {
+    1: dict(label="configs[0]", scene="box", mesh=None, normals=False, mode="shadow", width=1440, height=1440, spp=1,
+            nif=False, steps=20, warmup=3,
+            what="built-in 'box' scene, --render-mode shadow-trace (traceShadowRay: closest hit + shadow ray), 1 spp"),
+    2: dict(label="configs[1]", scene="box", mesh=None, normals=False, mode="path", width=1440, height=1440, spp=1000,
+            nif=True, steps=3, warmup=3,
+            what="built-in 'box' scene, path-trace RGB with NIF HDRI environment light (synthetic weights, seed 1442)"),
+    3: dict(label="configs[2]", scene=None, mesh="assets/test_scene.dae", normals=True, mode="path", width=1440,
+            height=1440, spp=4000, nif=False, steps=1, warmup=3,
+            what="assets/test_scene.dae --load-normals (8474 triangles, glass / mirror / emitters; 407 KB BVH: L2-resident), path-trace RGB"),
+    4: dict(label="configs[3]", scene="box", mesh=None, normals=False, mode="path", width=3840, height=2160, spp=256,
+            nif=False, steps=2, warmup=3,
+            what="assets/monkey_bust.glb inside the built-in 'box' scene (the GLB has no camera, SURVEY.md 8d), path-trace RGB, "
+                 "reference default 256 spp"),
+    5: dict(label="configs[4]", scene=None, mesh="assets/hdri_test.dae", normals=False, mode="path", width=8192,
+            height=8192, spp=1000, nif=True, steps=1, warmup=3,
+            what="assets/hdri_test.dae NIF-lit (open sky; synthetic weights, seed 1442), ray stream host-resident and "
+                 "streamed through the GPU in tiles"),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--width", type=int, default=1440)
-    ap.add_argument("--height", type=int, default=1440)
-    ap.add_argument("--samples", type=int, default=1000)
-    ap.add_argument("--scene", default="box")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configuration, 1-based")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--samples", type=int, default=None, help="override the configuration's spp (labelled in `config`)")
+    ap.add_argument("--scene", default=None)
     ap.add_argument("--no-nif", action="store_true", help="diagnostic only: drop the NIF environment light")
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--residency", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0, help="samples per NIF wavefront chunk (0 = auto)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the bounded CPU sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.cfg = cfg
+    args.steps = cfg["steps"] if args.steps is None else args.steps
+    args.warmup = cfg["warmup"] if args.warmup is None else args.warmup
+    args.width = cfg["width"] if args.width is None else args.width
+    args.height = cfg["height"] if args.height is None else args.height
+    args.spp_named = cfg["spp"]
+    args.samples = cfg["spp"] if args.samples is None else args.samples
+    args.mode = cfg["mode"]
+    args.scene = cfg["scene"] if args.scene is None else args.scene
+    args.use_nif = cfg["nif"] and not args.no_nif
+    return args
 
 
-def config_dict(args, n_gpus):
-    return {
-        "workload": f"built-in '{args.scene}' scene, path-trace RGB"
-                    + ("" if args.no_nif else " with NIF HDRI environment light (synthetic weights, seed 1442)")
-                    + f", {args.width}x{args.height}, {args.samples} spp (BASELINE.json configs[1])",
-        "scene": args.scene, "width": args.width, "height": args.height, "spp": args.samples,
+def load_scene(args, device=-1):
+    cfg = args.cfg
+    if cfg["mesh"] and args.scene is None:
+        s = HostScene.from_file(ROOT / cfg["mesh"], load_normals=cfg["normals"])
+    else:
+        s = HostScene.builtin(args.scene)
+    return s.configure(args.width, args.height, path_trace=args.mode == "path", samples=max(args.samples, 1), seed=1442,
+                       device=device)
+
+
+def config_dict(args, n_gpus, reference_sample=None):
+    cfg = args.cfg
+    named = (args.width, args.height, args.samples) == (cfg["width"], cfg["height"], cfg["spp"])
+    d = {
+        "workload": f"{cfg['what']}, {args.width}x{args.height}, {args.samples} spp (BASELINE.json {cfg['label']}"
+                    + ("" if named else f"; REDUCED from {cfg['width']}x{cfg['height']}, {cfg['spp']} spp") + ")",
+        "baseline_config": cfg["label"], "scene": args.scene or cfg["mesh"], "mode": args.mode,
+        "width": args.width, "height": args.height, "spp": args.samples,
         "max_path_length": 10, "roulette_start_depth": 3, "anti_alias": 0.25, "seed": 1442,
-        "nif": not args.no_nif,
+        "nif": bool(args.use_nif),
         "parallelism": f"ray-data-parallel: 8640-ray batches, batch i -> rank i % {n_gpus}, scene replicated",
-        "l2_policy": "inputs larger than L2 (174 MB ray stream per image vs 126 MB L2); no flush between steps",
+        "l2_policy": ("inputs larger than L2: a fresh copy of the ray stream per step from a ring of pre-initialised "
+                      "buffers (174 MB each vs 126 MB L2)" if args.mode == "shadow" else
+                      "inputs larger than L2 (ray stream + >= 4 GB of path state per chunk vs 126 MB L2); no flush between steps"),
     }
+    if reference_sample is not None:
+        # the CPU arm renders a bounded sample of this workload with the reference's kernels; it has no NIF stage
+        d["nif"] = False
+        d["reference_sample"] = reference_sample
+        d["workload"] += " -- CPU arm: bounded sample, see reference_sample; the reference CPU path has no NIF stage"
+    return d
 
 
 # ------------------------------------------------------------------------------------------------
@@ -175,34 +229,48 @@ def cpu_baseline(args, scene, nif, kind_pref=("port",), seconds=12.0):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": "no oracle library built"}
     orc = oracle_py.Oracle(kind)
     cores = os.cpu_count() or 1
-    use_nif = nif if (kind == "port" and not args.no_nif) else None
+    use_nif = nif if (kind == "port" and args.use_nif) else None
     w, h = args.width, args.height
-    full = init_ray_stream(w, h, scene.fov)
-    # bounded sample: every `stride`-th pixel of the full image (stratified over the whole frame), `spp` samples each
     rng = np.random.default_rng(0)
+    # bounded sample: rows of the frame (stratified over its height), generated directly as crop windows so that even
+    # the 8192^2 stream never has to exist on the host for this leg
+    def rows_sample(n_rows):
+        picks = np.sort(rng.choice(h, size=min(n_rows, h), replace=False))
+        return np.concatenate([init_ray_stream(w, h, scene.fov, window=(w, 1, 0, int(r))) for r in picks])
 
-    def run(stride, spp):
-        sel = np.ascontiguousarray(full[rng.integers(0, stride)::stride])
-        t0 = time.perf_counter()
-        cnt = orc.path_trace(scene, sel, first_sample=0, num_samples=spp, nif=use_nif, threads=cores)
-        return time.perf_counter() - t0, cnt, sel.size
+    if args.mode == "shadow":
+        def run(n_rows, _spp):
+            sel = rows_sample(n_rows)
+            t0 = time.perf_counter()
+            cnt = orc.shadow_trace(scene, sel, threads=cores)
+            return time.perf_counter() - t0, cnt, sel.size
+        what = "traceShadowRay"
+    else:
+        def run(n_rows, spp):
+            sel = rows_sample(n_rows)
+            t0 = time.perf_counter()
+            cnt = orc.path_trace(scene, sel, first_sample=0, num_samples=spp, nif=use_nif, threads=cores)
+            return time.perf_counter() - t0, cnt, sel.size
+        what = "pathTrace"
 
-    dt, cnt, npix = run(256, 2)  # probe (~16k samples)
-    rate = cnt["samples"] / max(dt, 1e-6)
-    target = max(int(rate * seconds), 20000)
-    spp = 4
-    stride = max(1, int(w * h * spp / target))
-    if stride == 1:  # fast host: keep every pixel and raise the sample count instead
-        spp = int(max(4, min(args.samples, target // (w * h))))
-    dt, cnt, npix = run(stride, spp)
+    spp = 1 if args.mode == "shadow" else 4
+    dt, cnt, npix = run(8, spp)  # probe
+    per_row = max(dt, 1e-6) / 8
+    rows = int(max(8, min(h, seconds / per_row)))
+    if rows == h and args.mode != "shadow":  # fast host: keep every row and raise the sample count instead
+        spp = int(max(4, min(args.samples, spp * seconds / (per_row * h))))
+    dt, cnt, npix = run(rows, spp)
     q = cnt["closest_hit_queries"] + cnt["occlusion_queries"]
+    samples = cnt["samples"] if args.mode != "shadow" else npix
     return {
         "value": q / dt / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-        "samples_per_s": cnt["samples"] / dt, "seconds": dt,
-        "sample": f"{npix} pixels (every {stride}th of the {w}x{h} frame) x {spp} spp = {cnt['samples']} samples, "
-                  f"{q} BVH queries in {dt:.2f} s; OpenMP dynamic schedule over rays, per-(pixel,sample) RNG streams"
+        "samples_per_s": samples / dt, "seconds": dt,
+        "sample": f"{what} over {rows} of the {h} rows of the {w}x{h} frame (stratified) x {spp} spp = {samples} samples, "
+                  f"{q} BVH queries in {dt:.2f} s; OpenMP dynamic schedule over rays"
+                  + ("" if args.mode == "shadow" else ", per-(pixel,sample) RNG streams")
                   + ("; NIF evaluated in fp32 on the CPU for escaped rays" if use_nif is not None else
-                     "; no NIF stage (the reference CPU path has none: escaped rays just stop, trace.cpp:171-174)"),
+                     ("" if args.mode == "shadow" else
+                      "; no NIF stage (the reference CPU path has none: escaped rays just stop, trace.cpp:171-174)")),
     }
 
 
@@ -211,12 +279,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene = HostScene.builtin(args.scene).configure(args.width, args.height, path_trace=True, samples=args.samples)
-    nif = NifWeights.synthetic(seed=1442)
+    scene = load_scene(args)
     per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     vals, base = [], None
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(args, scene, nif, kind_pref=("reference", "port"), seconds=per_step)
+        base = cpu_baseline(args, scene, None, kind_pref=("reference", "port"), seconds=per_step)
         if i >= args.warmup:
             vals.append(base)
     v = float(np.mean([b["value"] for b in vals]))
@@ -224,9 +291,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean([b["seconds"] for b in vals])) * 1e3,
-        "ms_per_full_step_extrapolated": args.width * args.height * args.samples / sps * 1e3,
+        "ms_per_full_step_extrapolated": args.width * args.height * max(args.samples, 1) / sps * 1e3,
         "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, args.gpus),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, args.gpus, reference_sample=base["sample"]),
         "samples_per_s": sps,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": base["cores"], "kind": base["kind"], "sample": base["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -260,11 +328,14 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     w, h, spp = args.width, args.height, args.samples
-    scene = HostScene.builtin(args.scene).configure(w, h, path_trace=True, samples=spp, seed=1442, device=local_rank)
-    nif = None if args.no_nif else NifWeights.synthetic(seed=1442)
-    full = init_ray_stream(w, h, scene.fov)
-    mine = batch_owner_mask(full.size, RAYS_PER_BATCH, world, rank)
-    shard = np.ascontiguousarray(full[mine])
+    shadow = args.mode == "shadow"
+    scene = load_scene(args, device=local_rank)
+    nif = NifWeights.synthetic(seed=1442) if args.use_nif else None
+    n_total = w * h
+    mine = batch_owner_mask(n_total, RAYS_PER_BATCH, world, rank)
+    # this rank's shard of the stream, generated row by row so the full 8192^2 stream never sits on the host twice
+    shard = np.concatenate([init_ray_stream(w, h, scene.fov, window=(w, r1 - r0, 0, r0))[mine[r0 * w:r1 * w]]
+                            for r0, r1 in ((r, min(r + 256, h)) for r in range(0, h, 256))])
     n_local = shard.size
     shard_bytes = n_local * capi.TRACE_RESULT.itemsize
 
@@ -274,18 +345,20 @@ def run_b200(args):
     params = dict(traversal=args.traversal, scene_residency=args.residency, samples_per_chunk=args.chunk)
 
     pristine = torch.from_numpy(shard.view(np.uint8)).cuda()
-    work = torch.empty_like(pristine)
-    pinned = torch.from_numpy(shard.view(np.uint8).copy()).pin_memory()
-    pinned_np = pinned.numpy().view(capi.TRACE_RESULT)
+    # Single-pass (shadow-trace) steps consume their input, so every timed step gets its own pre-initialised copy of the
+    # stream (up to 32; beyond that the copies are refreshed inside the timed region and the line says so).
+    ring_n = min(max(args.steps, 1), 32) if shadow else 1
+    works = [torch.empty_like(pristine) for _ in range(ring_n)]
+    work = works[0]
     gather_list = None
-    rgb_counts = [int(batch_owner_mask(full.size, RAYS_PER_BATCH, world, r).sum()) for r in range(world)]
+    rgb_counts = [int(batch_owner_mask(n_total, RAYS_PER_BATCH, world, r).sum()) for r in range(world)]
     stream = torch.cuda.current_stream().cuda_stream
 
-    def gather_rgb():
+    def gather_rgb(buf):
         """Final framebuffer gather (rgb of every ray) to rank 0 over NCCL."""
         if world == 1:
             return
-        rgb = work.view(n_local, 84)[:, :12].contiguous()
+        rgb = buf.view(n_local, 84)[:, :12].contiguous()
         nonlocal gather_list
         if rank == 0 and gather_list is None:
             gather_list = [torch.empty(c, 12, dtype=torch.uint8, device="cuda") for c in rgb_counts]
@@ -293,14 +366,16 @@ def run_b200(args):
 
     totals = {"queries": 0, "samples": 0, "escaped": 0, "launches": 0, "kernel_ms": 0.0}
 
-    def device_step(record):
-        work.copy_(pristine)
-        g.execute_device(work.data_ptr(), n_local, stream=stream, **params)
-        gather_rgb()
+    def device_step(record, k=0):
+        buf = works[k % ring_n]
+        if not shadow or k >= ring_n:
+            buf.copy_(pristine)
+        g.execute_device(buf.data_ptr(), n_local, stream=stream, **params)
+        gather_rgb(buf)
         if record:
             st = g.stats()
             totals["queries"] += st["closest_hit_queries"] + st["occlusion_queries"]
-            totals["samples"] += st["samples"]
+            totals["samples"] += st["samples"] if not shadow else n_local
             totals["escaped"] += st["escaped_samples"]
             totals["launches"] += st["kernel_launches"]
             totals["kernel_ms"] += st["kernel_ms"]
@@ -310,11 +385,13 @@ def run_b200(args):
     with ClockSampler(local_rank) as clocks:  # started before the warm-up so that it is running when the clock starts
         for _ in range(args.warmup):
             device_step(False)
+        for b in works:
+            b.copy_(pristine)
         barrier()
         clocks.mark_start()
         ev0.record()
-        for _ in range(args.steps):
-            device_step(True)
+        for k in range(args.steps):
+            device_step(True, k)
         ev1.record()
         barrier()
         clocks.mark_end()
@@ -322,25 +399,26 @@ def run_b200(args):
 
     # ---- end-to-end arm: host buffers through b200rt_trace ----
     # Every timed step renders a freshly initialised ray stream that already sits in page-locked host memory (a ring of
-    # up to 4 streams prepared before the clock starts; rgb is a running sum, so a stream that comes round again after
-    # the ring wraps is the same work). Inside the timed region: H2D of the stream, all kernels, D2H of the results.
-    ring = [pinned_np] + [torch.empty(n_local * 84, dtype=torch.uint8).pin_memory().numpy().view(capi.TRACE_RESULT)
-                          for _ in range(min(args.steps, 4) - 1)]
+    # streams prepared before the clock starts; rgb is a running sum, so a path-traced stream that comes round again
+    # after the ring wraps is the same work). Inside the timed region: H2D of the stream, all kernels, D2H of the results.
+    e2e_ring = max(1, min(args.steps, 32 if shadow else 4, int((8 << 30) // max(shard_bytes, 1))))
+    ring = [torch.empty(n_local * 84, dtype=torch.uint8).pin_memory().numpy().view(capi.TRACE_RESULT) for _ in range(e2e_ring)]
+    e2e_steps = args.steps if (not shadow or args.steps <= e2e_ring) else e2e_ring
 
     def e2e_step(buf):
         g.execute(buf, **params)
         if world > 1:
             work.view(n_local, 84)[:, :12].copy_(torch.from_numpy(buf.view(np.uint8).reshape(n_local, 84)[:, :12]).cuda())
-            gather_rgb()
+            gather_rgb(work)
 
-    pinned_np[:] = shard
-    e2e_step(pinned_np)  # warm-up of the host-buffer path (staging buffers, first-touch)
+    ring[0][:] = shard
+    e2e_step(ring[0])  # warm-up of the host-buffer path (staging buffers, first-touch)
     for buf in ring:
         buf[:] = shard
     barrier()
     t0 = time.perf_counter()
     e2e_queries = 0
-    for k in range(args.steps):
+    for k in range(e2e_steps):
         e2e_step(ring[k % len(ring)])
         st = g.stats()
         e2e_queries += st["closest_hit_queries"] + st["occlusion_queries"]
@@ -362,7 +440,7 @@ def run_b200(args):
         value = queries / (dev_ms * 1e-3) / 1e6
         e2e_value = e2e_queries / (e2e_ms * 1e-3) / 1e6
         # per-kernel breakdown from one extra instrumented step (not timed)
-        prof = kernel_breakdown(g, work, pristine, n_local, stream, params, nif)
+        prof = kernel_breakdown(g, work, pristine, n_local, stream, params, shadow)
         flops_per_lookup = nif.flops_per_sample() if nif is not None else 0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -370,13 +448,16 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, world),
             "samples_per_s": samples / (dev_ms * 1e-3),
             "bvh_queries_per_sample": queries / max(samples, 1), "escaped_fraction": escaped / max(samples, 1),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": shard_bytes * 1 if world == 1 else full.size * 84,
-                    "d2h_bytes_per_step": shard_bytes * 1 if world == 1 else full.size * 84, "ms_per_step": e2e_ms / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_total * 84, "d2h_bytes_per_step": n_total * 84,
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "note": "ray stream in page-locked host memory; tiles pipelined H2D || kernels || D2H inside b200rt_trace"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "peaks": peaks,
         }
-        line.update(rooflines(prof, peaks, n_local, spp, flops_per_lookup, line["clocks"].get("sm_mhz")))
+        if shadow and args.steps > ring_n:
+            line["config"]["l2_policy"] += f"; steps beyond {ring_n} refresh their copy inside the timed region"
+        line.update(rooflines(prof, peaks, n_local, spp, flops_per_lookup, line["clocks"].get("sm_mhz"), shadow))
         if not args.skip_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args, scene, nif, kind_pref=("port",), seconds=args.cpu_seconds)
         elif world > 1:
@@ -388,7 +469,7 @@ def run_b200(args):
     g.close()
 
 
-def kernel_breakdown(g, work, pristine, n_local, stream, params, nif):
+def kernel_breakdown(g, work, pristine, n_local, stream, params, shadow):
     """Device time of the trace kernel alone vs the whole step, with CUDA events on the launching stream."""
     import torch
 
@@ -403,7 +484,8 @@ def kernel_breakdown(g, work, pristine, n_local, stream, params, nif):
     out["queries"] = st["closest_hit_queries"] + st["occlusion_queries"]
     # work counters (node visits / primitive tests) from a reduced-spp instrumented run, scaled per query
     work.copy_(pristine)
-    g.execute_device(work.data_ptr(), n_local, stream=stream, **dict(params, count_visits=1, num_samples=8))
+    extra = {} if shadow else {"num_samples": 8}
+    g.execute_device(work.data_ptr(), n_local, stream=stream, **dict(params, count_visits=1, **extra))
     sc = g.stats()
     q8 = max(sc["closest_hit_queries"] + sc["occlusion_queries"], 1)
     out["node_visits_per_query"] = sc["node_visits"] / q8
@@ -412,7 +494,7 @@ def kernel_breakdown(g, work, pristine, n_local, stream, params, nif):
     return out
 
 
-def rooflines(prof, peaks, n_local, spp, flops_per_lookup, sm_mhz=None):
+def rooflines(prof, peaks, n_local, spp, flops_per_lookup, sm_mhz=None, shadow=False):
     """Three regimes: ray-stream HBM, traversal issue rate, NIF tensor cores."""
     import torch
 
@@ -433,25 +515,28 @@ def rooflines(prof, peaks, n_local, spp, flops_per_lookup, sm_mhz=None):
     nl = max(prof["nif_kernel_launches"], 1)
     tl = max(prof["trace_kernel_launches"], 1)
     wavefront = prof.get("shade_kernel_launches", 0) > 0
-    trace_name = "wf_trace_kernel" if wavefront else "path_trace_kernel"
+    trace_name = "shadow_trace_kernel" if shadow else ("wf_trace_kernel" if wavefront else "path_trace_kernel")
     tr = traffic.get(trace_name) or {}
-    unit_note = "B per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)"
+    unit_note = "B per step, summed over the step's launches (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)"
     kernels = [
         {"kernel": trace_name, "bound": "issue", "share_of_step": trace_s / step_s,
          "launches_per_step": prof["trace_kernel_launches"], "avg_launch_ms": trace_s * 1e3 / tl,
          "algorithmic_lane_ops_per_launch": lane_ops / tl, "achieved": lane_ops / trace_s / 1e12,
          "peak": issue_peak / 1e12, "unit": "Tlane-op/s", "frac": lane_ops / trace_s / issue_peak,
          "node_visits_per_query": prof["node_visits_per_query"], "prim_tests_per_query": prof["prim_tests_per_query"],
-         "sm_clock_mhz_for_peak": sm_clock_hz / 1e6, "traffic": tr.get("dram_bytes_per_launch"), "traffic_unit": unit_note,
-         "note": ("one launch per bounce and chunk; launches of late bounces are nearly empty" if wavefront else
+         "sm_clock_mhz_for_peak": sm_clock_hz / 1e6, "traffic": tr.get("dram_bytes_per_step"), "traffic_unit": unit_note,
+         "note": ("single pass over the TraceResult stream: closest hit + shadow ray per camera ray" if shadow else
+                  "one launch per bounce and chunk; launches of late bounces are nearly empty" if wavefront else
                   "one launch per chunk: camera ray, traversal and shading of every bounce")},
-        {"kernel": "nif_mlp_kernel", "bound": "tensor", "share_of_step": nif_s / step_s if nif_flops else 0.0,
-         "launches_per_step": prof["nif_kernel_launches"], "avg_launch_ms": nif_s * 1e3 / nl,
-         "algorithmic_flops_per_launch": nif_flops / nl, "achieved": nif_flops / nif_s / 1e12 if nif_flops else 0.0,
-         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-         "frac": nif_flops / nif_s / 1e12 / peaks["bf16_tflops_sustained"] if nif_flops else 0.0,
-         "traffic": (traffic.get("nif_mlp_kernel") or {}).get("dram_bytes_per_launch"), "traffic_unit": unit_note},
     ]
+    if not shadow:
+        kernels.append(
+            {"kernel": "nif_mlp_kernel", "bound": "tensor", "share_of_step": nif_s / step_s if nif_flops else 0.0,
+             "launches_per_step": prof["nif_kernel_launches"], "avg_launch_ms": nif_s * 1e3 / nl,
+             "algorithmic_flops_per_launch": nif_flops / nl, "achieved": nif_flops / nif_s / 1e12 if nif_flops else 0.0,
+             "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+             "frac": nif_flops / nif_s / 1e12 / peaks["bf16_tflops_sustained"] if nif_flops else 0.0,
+             "traffic": (traffic.get("nif_mlp_kernel") or {}).get("dram_bytes_per_step"), "traffic_unit": unit_note})
     if wavefront:
         # wf_shade: HBM-bound on the path record. Algorithmic bytes per path-bounce: 84 B read (queue id, hit, origin,
         # direction, throughput, RNG; only the 16 B hit at bounce 0, whose camera ray is recomputed) + 68 B written for
@@ -461,15 +546,17 @@ def rooflines(prof, peaks, n_local, spp, flops_per_lookup, sm_mhz=None):
         sl = max(prof["shade_kernel_launches"], 1)
         kernels.append({"kernel": "wf_shade_kernel", "bound": "hbm", "share_of_step": shade_s / step_s,
                         "launches_per_step": prof["shade_kernel_launches"], "avg_launch_ms": shade_s * 1e3 / sl,
-                        "algorithmic_bytes_per_launch": shade_bytes / sl, "achieved": shade_bytes / shade_s / 1e9,
+                        "algorithmic_bytes_per_step": shade_bytes, "achieved": shade_bytes / shade_s / 1e9,
                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": shade_bytes / shade_s / 1e9 / peaks["hbm_gbs"],
-                        "traffic": (traffic.get("wf_shade_kernel") or {}).get("dram_bytes_per_launch"), "traffic_unit": unit_note})
+                        "traffic": (traffic.get("wf_shade_kernel") or {}).get("dram_bytes_per_step"), "traffic_unit": unit_note})
     kernels.append(
         {"kernel": "TraceResult stream in/out", "bound": "hbm", "algorithmic_bytes_per_step": stream_bytes,
          "achieved": stream_bytes / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
          "frac": stream_bytes / step_s / 1e9 / peaks["hbm_gbs"],
-         "note": "168 B/ray/render amortised over all spp: HBM is idle by design in a multi-sample render"})
-    dominant = kernels[0] if trace_s >= nif_s or not nif_flops else kernels[1]
+         "note": ("168 B/ray/render; the single-pass kernel is bound by traversal issue slots, not by this stream "
+                  "(see the issue entry)" if shadow else
+                  "168 B/ray/render amortised over all spp: HBM is idle by design in a multi-sample render")})
+    dominant = kernels[0] if (shadow or trace_s >= nif_s or not nif_flops) else kernels[1]
     roof = {"kernel": dominant["kernel"], "bound": dominant["bound"], "achieved": dominant["achieved"],
             "peak": dominant["peak"], "unit": dominant["unit"], "frac": dominant["frac"],
             "traffic": dominant.get("traffic"), "peak_source": peaks["source"],
