@@ -100,7 +100,13 @@ typedef struct b200rt_trace_params {
                                 * tracer starts from the parked hits: same rays, same hits, same results. Measured on
                                 * the box scene: pre-pass 4.5 ms + path tracer 47.5 ms vs 52.0 ms without -- no net
                                 * gain, because a warp's cost per bounce is its slowest bounce ray either way */
-  uint32_t reserved[4];
+  uint32_t batch_stride;       /* b200rt_trace only. 0 / 1 = the whole stream. R > 1: this call renders the ray batches
+                                * first_batch, first_batch + R, ... of the caller's stream in place (batch i -> replica
+                                * i % R, src/IpuScene.cpp:676-684); R scenes on R devices can share one host stream from
+                                * R threads without regrouping it. The callback's batch_index is the batch's index in
+                                * the whole stream (= k * R + replica, src/RayCallback.cpp:8-24) */
+  uint32_t first_batch;
+  uint32_t reserved[2];
 } b200rt_trace_params;
 
 /* Counters of the last trace (device-side counted, exact). */
@@ -123,10 +129,12 @@ typedef struct b200rt_trace_stats {
   uint64_t shade_kernel_launches;
 } b200rt_trace_stats;
 
-/* Called once per finished ray batch with (batch_index, rays, n, user).
+/* Called once per finished ray batch with (batch_index, rays, n, user), as soon as that batch's
+ * device->host copy has landed and while later tiles are still being traced.
  * Mirrors IpuScene::RayCallbackFn (include/IpuScene.hpp:31) / RayCallback::fetch
- * (src/RayCallback.cpp:8-24). Invoked on a library-owned host thread; must be
- * thread-safe and must not call back into the library. */
+ * (src/RayCallback.cpp:8-24). Invoked on a CUDA-owned host thread (cudaLaunchHostFunc), NOT on the
+ * caller's thread: it must be thread-safe and must not call this library or any CUDA API.
+ * All callbacks have returned when b200rt_trace returns. */
 typedef void (*b200rt_ray_cb)(size_t batch_index, const void* rays, size_t n, void* user);
 
 /* --- library --- */
@@ -134,6 +142,8 @@ int         b200rt_abi_version(void);
 const char* b200rt_last_error(void);
 /* Number of usable sm_100 devices (0 on a CPU-only host; never an error). */
 int         b200rt_device_count(void);
+/* CUDA ordinal of the index-th usable sm_100 device (for b200rt_scene_desc.device), or -1. */
+int         b200rt_device_ordinal(int index);
 
 /* --- scene lifetime: IpuScene ctor/dtor (src/IpuScene.cpp:24-64) --- */
 int  b200rt_scene_create(const b200rt_scene_desc* desc, b200rt_scene** out);

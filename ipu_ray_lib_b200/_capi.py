@@ -77,7 +77,8 @@ class TraceParams(C.Structure):
         ("first_sample", C.c_uint32), ("num_samples", C.c_uint32),
         ("rays_per_batch", C.c_uint32), ("traversal", C.c_uint32),
         ("scene_residency", C.c_uint32), ("samples_per_chunk", C.c_uint32),
-        ("count_visits", C.c_uint32), ("primary_pass", C.c_uint32), ("reserved", C.c_uint32 * 4),
+        ("count_visits", C.c_uint32), ("primary_pass", C.c_uint32),
+        ("batch_stride", C.c_uint32), ("first_batch", C.c_uint32), ("reserved", C.c_uint32 * 2),
     ]
 
 
@@ -121,7 +122,7 @@ RAY_CALLBACK = C.CFUNCTYPE(None, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
 
 # Every symbol include/b200rt.h declares; tests check the built library exports each one.
 B200RT_SYMBOLS = [
-    "b200rt_abi_version", "b200rt_last_error", "b200rt_device_count",
+    "b200rt_abi_version", "b200rt_last_error", "b200rt_device_count", "b200rt_device_ordinal",
     "b200rt_scene_create", "b200rt_scene_destroy",
     "b200rt_scene_load_nif", "b200rt_scene_set_hdri_rotation", "b200rt_scene_set_max_nif_batch_size",
     "b200rt_nif_eval", "b200rt_trace", "b200rt_trace_device",
@@ -141,7 +142,9 @@ _scene_lib = None
 
 
 def lib_path() -> Path:
-    return PKG_DIR / "libb200rt.so"
+    # B200RT_LIB selects another build of the same ABI (`make experiments`: libb200rt_exp.so); measurements only
+    override = os.environ.get("B200RT_LIB")
+    return Path(override) if override else PKG_DIR / "libb200rt.so"
 
 
 def scene_lib_path() -> Path:
@@ -160,6 +163,8 @@ def lib() -> C.CDLL:
         L.b200rt_abi_version.restype = C.c_int
         L.b200rt_last_error.restype = C.c_char_p
         L.b200rt_device_count.restype = C.c_int
+        L.b200rt_device_ordinal.argtypes = [C.c_int]
+        L.b200rt_device_ordinal.restype = C.c_int
         L.b200rt_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
         L.b200rt_scene_destroy.argtypes = [C.c_void_p]
         L.b200rt_scene_destroy.restype = None

@@ -18,6 +18,9 @@
 #include "../../include/b200rt.h"
 #include "nif.cuh"
 #include "scene_tables.hpp"
+#ifdef B200RT_EXPERIMENT_SORT
+#include <cub/device/device_radix_sort.cuh>
+#endif
 #include "trace_kernels.cuh"
 #include "wavefront.cuh"
 
@@ -88,6 +91,7 @@ struct b200rt_scene {
   DeviceBuffer wfRayO, wfRayD, wfNrm, wfThr, wfRng, wfHitA, wfHitB, wfQ0, wfQ1, wfCounts;  // wavefront path state
   b200rt_trace_stats stats{};
   float hdriRotationDegrees = 0.f;
+  float rootBox[6] = {0.f, 0.f, 0.f, 1.f, 1.f, 1.f};  // min, extent of the root node
   size_t maxNifBatch = 0;
   rt::NifModel* nif = nullptr;
 
@@ -259,13 +263,25 @@ float host_tan_half_fov(float fov) {
   return s / c;
 }
 
-// Renders d_rays[0..n) in place on sc.stream. Adds to sc.stats (kernel time via events).
-int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, size_t n, cudaStream_t stream) {
+// One b200rt_trace / b200rt_trace_device call: kernels are enqueued tile by tile on sc.stream without any host
+// synchronisation; the statistics (per-kernel CUDA-event spans, device-side counters) are collected once at the end.
+struct RenderRun {
+  KernelTimer timer;
+  uint64_t launches = 0;
+};
+
+int render_begin(b200rt_scene& sc, RenderRun&) {
+  CU_TRY(cudaMemsetAsync(sc.counters.p, 0, sizeof(rt::DeviceCounters), sc.stream));
+  CU_TRY(cudaEventRecord(sc.evStart, sc.stream));
+  return B200RT_OK;
+}
+
+// Enqueues the render of d_rays[0..n) (in place) on sc.stream.
+int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, size_t n, RenderRun& run) {
   if (n == 0) return B200RT_OK;
   if (n > 0xFFFFFFFFull) return fail(B200RT_ERR_INVALID_ARG, "ray stream longer than 2^32 rays");
-  cudaStream_t saved = sc.stream;
-  if (stream) sc.stream = stream;
-  struct Restore { b200rt_scene& s; cudaStream_t v; ~Restore() { s.stream = v; } } restore{sc, saved};
+  KernelTimer& timer = run.timer;
+  uint64_t& launches = run.launches;
 
   // auto = wavefront (measured 30 % faster than the megakernel); its packed record holds the bounce in 8 bits.
   // traversal 3 (the state-machine megakernel of round 1, measured slower) is gone: it selects the wavefront tracer too.
@@ -279,10 +295,6 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
   a.workCounter = (uint32_t*)sc.workCounter.p;
   a.counters = (rt::DeviceCounters*)sc.counters.p;
   a.nodeBytes = sc.nodeBytes;
-  CU_TRY(cudaMemsetAsync(sc.counters.p, 0, sizeof(rt::DeviceCounters), sc.stream));
-  CU_TRY(cudaEventRecord(sc.evStart, sc.stream));
-  uint64_t launches = 0;
-  KernelTimer timer;
 
   if (!sc.desc.path_trace) {
     const bool dflt = p.light_pos[0] == 0.f && p.light_pos[1] == 0.f && p.light_pos[2] == 0.f && p.ambient == 0.f;
@@ -291,8 +303,22 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
     a.lightZ = dflt ? -1060.f : p.light_pos[2];
     a.ambient = dflt ? .05f : p.ambient;
     CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 4, sc.stream));
+    // near-first renders of a 16-byte aligned stream: tiles moved by the TMA engine (shadow_stream_kernel)
+    static const bool envTma = [] { const char* e = std::getenv("B200RT_SHADOW_TMA"); return !e || e[0] != '0'; }();
+    const bool tma = envTma && L.ordered && (reinterpret_cast<uintptr_t>(d_rays) % 16u) == 0u;
     timer.begin(KernelTimer::TRACE, sc.stream);
-    CU_TRY(run_shadow(sc, L, a));
+    if (tma) {
+      const size_t ring = rt::kStreamRingBytes;
+      const bool shared = p.scene_residency != 2 && (size_t)sc.pairBytes + ring <= (size_t)sc.maxSmemOptin;
+      const size_t smem = (shared ? (size_t)sc.pairBytes : 0) + ring;
+      auto k = shared ? (L.count ? rt::shadow_stream_kernel<true, true> : rt::shadow_stream_kernel<true, false>)
+                      : (L.count ? rt::shadow_stream_kernel<false, true> : rt::shadow_stream_kernel<false, false>);
+      CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<sc.numSMs, rt::kStreamThreads, smem, sc.stream>>>(a);
+      CU_TRY(cudaGetLastError());
+    } else {
+      CU_TRY(run_shadow(sc, L, a));
+    }
     timer.end(sc.stream);
     launches += 1;
   } else {
@@ -405,6 +431,28 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
             CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + 2, 0, 4, sc.stream));            // fetch cursor
             CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + (w.qIn ^ 1), 0, 4, sc.stream));  // next queue size
             const bool first = b == 0;  // bounce 0: camera rays are generated in the kernels, the queue is the identity
+            w.b.traceOrder = nullptr;
+#ifdef B200RT_EXPERIMENT_SORT
+            static const int envSort = [] { const char* e = std::getenv("B200RT_SORT"); return e ? std::atoi(e) : 0; }();
+            if (envSort && !first) {
+              // EXPERIMENT: wf_trace takes the bounce's rays sorted by (origin cell, direction bin); CUB radix sort
+              static DeviceBuffer keysIn, keysOut, idsIn, idsOut, tmp;
+              const size_t P = w.numPaths;
+              CU_TRY(keysIn.reserve(P * 4)); CU_TRY(keysOut.reserve(P * 4)); CU_TRY(idsIn.reserve(P * 4)); CU_TRY(idsOut.reserve(P * 4));
+              size_t tmpBytes = 0;
+              cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (uint32_t*)keysIn.p, (uint32_t*)keysOut.p, (uint32_t*)idsIn.p,
+                                              (uint32_t*)idsOut.p, (int)P, 0, 21, sc.stream);
+              CU_TRY(tmp.reserve(tmpBytes));
+              const float* root = sc.rootBox;
+              timer.begin(KernelTimer::ACCUM, sc.stream);  // booked under "accumulate" in the experiment
+              rt::wf_sort_key_kernel<<<sc.numSMs * 8, 256, 0, sc.stream>>>(w, (uint32_t*)keysIn.p, (uint32_t*)idsIn.p,
+                  make_float3(root[0], root[1], root[2]), make_float3(1.f / root[3], 1.f / root[4], 1.f / root[5]));
+              cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, (uint32_t*)keysIn.p, (uint32_t*)keysOut.p, (uint32_t*)idsIn.p,
+                                              (uint32_t*)idsOut.p, (int)P, 0, 21, sc.stream);
+              timer.end(sc.stream);
+              w.b.traceOrder = (const uint32_t*)idsOut.p;
+            }
+#endif
             timer.begin(KernelTimer::TRACE, sc.stream);
             {
               cudaError_t e;
@@ -469,11 +517,28 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
       }
     }
   }
+  return B200RT_OK;
+}
+
+// Path-traced streams much longer than a frame are rendered in ray tiles, so that the per-path state of a chunk
+// (tile rays x samples per chunk) keeps its ~64 M-path size instead of the chunk shrinking to a couple of samples
+// (8192^2 rays: 2 samples per chunk = ~10 000 tiny launches per 1000 spp). Per-(pixel, sample) RNG streams make the
+// result independent of the tiling.
+int render_enqueue(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, size_t n, RenderRun& run) {
+  constexpr size_t kTile = (size_t)1 << 21;
+  if (!sc.desc.path_trace || n <= 2 * kTile) return render_tile(sc, p, d_rays, n, run);
+  for (size_t off = 0; off < n; off += kTile)
+    if (int rc = render_tile(sc, p, d_rays + off * rt::TR_WORDS, std::min(kTile, n - off), run)) return rc;
+  return B200RT_OK;
+}
+
+int render_end(b200rt_scene& sc, RenderRun& run) {
   CU_TRY(cudaEventRecord(sc.evStop, sc.stream));
   CU_TRY(cudaStreamSynchronize(sc.stream));
   float ms = 0.f;
   CU_TRY(cudaEventElapsedTime(&ms, sc.evStart, sc.evStop));
-  timer.collect(sc.stats);
+  run.timer.collect(sc.stats);
+  const uint64_t launches = run.launches;
   rt::DeviceCounters hc{};
   CU_TRY(cudaMemcpy(&hc, sc.counters.p, sizeof(hc), cudaMemcpyDeviceToHost));
   sc.stats.closest_hit_queries += hc.closest;
@@ -485,6 +550,18 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
   sc.stats.kernel_ms += ms;
   sc.stats.kernel_launches += launches;
   return B200RT_OK;
+}
+
+// Renders d_rays[0..n) in place on `stream` (nullptr = the scene's own stream) and waits for it.
+int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, size_t n, cudaStream_t stream) {
+  if (n == 0) return B200RT_OK;
+  cudaStream_t saved = sc.stream;
+  if (stream) sc.stream = stream;
+  struct Restore { b200rt_scene& s; cudaStream_t v; ~Restore() { s.stream = v; } } restore{sc, saved};
+  RenderRun run;
+  if (int rc = render_begin(sc, run)) return rc;
+  if (int rc = render_enqueue(sc, p, d_rays, n, run)) return rc;
+  return render_end(sc, run);
 }
 
 }  // namespace
@@ -503,6 +580,16 @@ int b200rt_device_count(void) {
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) usable++;
   }
   return usable;
+}
+
+int b200rt_device_ordinal(int index) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (int i = 0, usable = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10 && usable++ == index) return i;
+  }
+  return -1;
 }
 
 int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
@@ -572,6 +659,15 @@ int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
   sc->dev.rootRef = tables.pairs.rootRef;
   sc->dev.rootGeom = tables.pairs.rootGeom;
   sc->dev.boundsFinite = tables.pairs.boundsFinite ? 1u : 0u;
+  {
+    struct Node { float mn[3]; uint32_t x; uint16_t d[3]; uint16_t g; };
+    const Node& r = *static_cast<const Node*>(d->bvh_nodes);
+    for (int k = 0; k < 3; ++k) {
+      sc->rootBox[k] = r.mn[k];
+      const float e = rt::half_bits_to_float(r.d[k]);
+      sc->rootBox[3 + k] = e > 0.f ? e : 1.f;
+    }
+  }
   // the scalars stay; the host pointers must not be used after creation
   sc->desc.geometry = sc->desc.mesh_info = sc->desc.mesh_tris = sc->desc.mesh_verts = sc->desc.mesh_normals = nullptr;
   sc->desc.mat_ids = nullptr; sc->desc.materials = sc->desc.bvh_nodes = nullptr;
@@ -636,6 +732,26 @@ int b200rt_trace_device(b200rt_scene* sc, const b200rt_trace_params* params, voi
   return rc;
 }
 
+// Host-resident stream: the reference's load / compute / save pipeline (src/IpuScene.cpp:583-618: while batch k is
+// traced, batch k+1 streams in and batch k-1 streams out; >= 2 batches per replica, :102-105). Here the stream is cut
+// into tiles of whole ray batches; tile k+1's host->device copy (copy-in stream), tile k's kernels (the scene's stream)
+// and tile k-1's device->host copy (copy-out stream) overlap, ordered by events, over a ring of three device buffers.
+// A callback is invoked per finished ray batch from a CUDA-owned host thread (cudaLaunchHostFunc on the copy-out
+// stream), like RayCallback::fetch on a Poplar runtime thread (src/RayCallback.cpp:8-24).
+namespace {
+struct CallbackJob {
+  b200rt_ray_cb cb;
+  void* user;
+  size_t index;
+  const void* rays;
+  size_t n;
+};
+void CUDART_CB run_callback_job(void* p) {
+  const CallbackJob* j = static_cast<const CallbackJob*>(p);
+  j->cb(j->index, j->rays, j->n, j->user);
+}
+}  // namespace
+
 int b200rt_trace(b200rt_scene* sc, const b200rt_trace_params* params, void* rays, size_t n, b200rt_ray_cb cb,
                  void* user) {
   if (!sc || (!rays && n)) return fail(B200RT_ERR_INVALID_ARG, "null argument");
@@ -644,48 +760,113 @@ int b200rt_trace(b200rt_scene* sc, const b200rt_trace_params* params, void* rays
   if (params) p = *params;
   sc->stats = b200rt_trace_stats{};
   if (n == 0) return B200RT_OK;
-  const size_t bytes = n * 84;
-  CU_TRY(sc->rays.reserve(bytes));
+  if (n > 0xFFFFFFFFull) return fail(B200RT_ERR_INVALID_ARG, "ray stream longer than 2^32 rays");
 
-  // host -> HBM (the reference's copyToRemoteBuffer, src/IpuScene.cpp:676-684; untimed there, timed here)
-  cudaEvent_t e0, e1;
-  CU_TRY(cudaEventCreate(&e0));
-  CU_TRY(cudaEventCreate(&e1));
-  struct Ev { cudaEvent_t a, b; ~Ev() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev{e0, e1};
-  CU_TRY(cudaEventRecord(e0, sc->stream));
-  CU_TRY(cudaMemcpyAsync(sc->rays.p, rays, bytes, cudaMemcpyHostToDevice, sc->stream));
-  CU_TRY(cudaEventRecord(e1, sc->stream));
-  CU_TRY(cudaStreamSynchronize(sc->stream));
-  float ms = 0.f;
-  CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-  sc->stats.h2d_ms = ms;
+  // The batches this call renders: all of them, or (multi-replica callers) every `batch_stride`-th one starting at
+  // `first_batch` -- batch i -> replica i % R, src/IpuScene.cpp:676-684 -- read from and written back to their places in
+  // the caller's stream, so that R replicas share one host stream without any host-side regrouping.
+  // Tiles are made of whole batches (rays per batch = raysPerWorker * 6 * 1440 per replica, src/IpuScene.cpp:78-108).
+  const size_t batch = p.rays_per_batch ? p.rays_per_batch : 8640;
+  const size_t stride = p.batch_stride ? p.batch_stride : 1, firstBatch = p.first_batch;
+  const size_t allBatches = (n + batch - 1) / batch;
+  const size_t myBatches = firstBatch < allBatches ? (allBatches - firstBatch + stride - 1) / stride : 0;
+  if (myBatches == 0) return B200RT_OK;
+  static const size_t envTile = [] { const char* e = std::getenv("B200RT_TILE_RAYS"); return e ? (size_t)std::atoll(e) : (size_t)0; }();
+  // single-pass renders are bound by the PCIe copies: small tiles so that the two copy directions overlap almost
+  // completely; multi-sample renders are bound by the kernels: large tiles keep the per-bounce launches large
+  const size_t wantTile = envTile ? envTile : (sc->desc.path_trace ? (size_t)1 << 20 : (size_t)1 << 17);
+  const size_t tileBatches = std::max<size_t>(1, wantTile / batch);
+  const size_t numTiles = (myBatches + tileBatches - 1) / tileBatches;
+  constexpr int kRing = 3;
+  const int ring = (int)std::min<size_t>(kRing, numTiles);
+  const size_t tileBytes = std::min(tileBatches, myBatches) * batch * 84;
+  CU_TRY(sc->rays.reserve(tileBytes * ring));
+
+  struct Pipe {
+    cudaStream_t in = nullptr, out = nullptr;
+    cudaEvent_t evIn[kRing]{}, evRender[kRing]{}, evOut[kRing]{};
+    std::vector<cudaEvent_t> timing;  // per tile: h2d begin, h2d end, d2h begin, d2h end
+    ~Pipe() {
+      for (int i = 0; i < kRing; ++i)
+        for (cudaEvent_t e : {evIn[i], evRender[i], evOut[i]})
+          if (e) cudaEventDestroy(e);
+      for (cudaEvent_t e : timing) cudaEventDestroy(e);
+      if (in) cudaStreamDestroy(in);
+      if (out) cudaStreamDestroy(out);
+    }
+  } pipe;
+  CU_TRY(cudaStreamCreateWithFlags(&pipe.in, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&pipe.out, cudaStreamNonBlocking));
+  for (int i = 0; i < ring; ++i) {
+    CU_TRY(cudaEventCreateWithFlags(&pipe.evIn[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&pipe.evRender[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&pipe.evOut[i], cudaEventDisableTiming));
+  }
+  auto timing_event = [&](cudaStream_t st) -> cudaError_t {
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreate(&e);
+    if (rc != cudaSuccess) return rc;
+    pipe.timing.push_back(e);
+    return cudaEventRecord(e, st);
+  };
+  std::vector<CallbackJob> jobs;
+  if (cb) jobs.resize(myBatches);
+  // rays of my j-th batch
+  auto batch_lo = [&](size_t j) { return (firstBatch + j * stride) * batch; };
+  auto batch_len = [&](size_t j) { return std::min(batch, n - batch_lo(j)); };
 
   const auto t0 = std::chrono::steady_clock::now();
-  if (int rc = render_device(*sc, p, (float*)sc->rays.p, n, nullptr)) return rc;
-  sc->stats.trace_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-
-  // HBM -> host, batch by batch so a callback sees the reference's batch granularity
-  // (rays per batch = raysPerWorker * 6 * 1440 per replica, src/IpuScene.cpp:78-108).
-  const size_t batch = p.rays_per_batch ? p.rays_per_batch : 8640;
-  CU_TRY(cudaEventRecord(e0, sc->stream));
-  if (!cb) {
-    CU_TRY(cudaMemcpyAsync(rays, sc->rays.p, bytes, cudaMemcpyDeviceToHost, sc->stream));
-    CU_TRY(cudaEventRecord(e1, sc->stream));
-    CU_TRY(cudaStreamSynchronize(sc->stream));
-  } else {
-    size_t index = 0;
-    for (size_t off = 0; off < n; off += batch, ++index) {
-      const size_t cnt = std::min(batch, n - off);
-      char* dst = (char*)rays + off * 84;
-      CU_TRY(cudaMemcpyAsync(dst, (char*)sc->rays.p + off * 84, cnt * 84, cudaMemcpyDeviceToHost, sc->stream));
-      CU_TRY(cudaStreamSynchronize(sc->stream));
-      cb(index, dst, cnt, user);
+  RenderRun run;
+  if (int rc = render_begin(*sc, run)) return rc;
+  for (size_t k = 0; k < numTiles; ++k) {
+    const int slot = (int)(k % (size_t)ring);
+    const size_t j0 = k * tileBatches, j1 = std::min(myBatches, j0 + tileBatches);
+    size_t cnt = 0;
+    for (size_t j = j0; j < j1; ++j) cnt += batch_len(j);
+    char* dbuf = (char*)sc->rays.p + (size_t)slot * tileBytes;
+    // host -> HBM (the reference's copyToRemoteBuffer, src/IpuScene.cpp:676-684), once the slot's last read-back is done
+    if (k >= (size_t)ring) CU_TRY(cudaStreamWaitEvent(pipe.in, pipe.evOut[slot], 0));
+    CU_TRY(timing_event(pipe.in));
+    if (stride == 1) {
+      CU_TRY(cudaMemcpyAsync(dbuf, (char*)rays + batch_lo(j0) * 84, cnt * 84, cudaMemcpyHostToDevice, pipe.in));
+    } else {
+      for (size_t j = j0; j < j1; ++j)
+        CU_TRY(cudaMemcpyAsync(dbuf + (j - j0) * batch * 84, (char*)rays + batch_lo(j) * 84, batch_len(j) * 84,
+                               cudaMemcpyHostToDevice, pipe.in));
     }
-    CU_TRY(cudaEventRecord(e1, sc->stream));
-    CU_TRY(cudaStreamSynchronize(sc->stream));
+    CU_TRY(timing_event(pipe.in));
+    CU_TRY(cudaEventRecord(pipe.evIn[slot], pipe.in));
+    // kernels
+    CU_TRY(cudaStreamWaitEvent(sc->stream, pipe.evIn[slot], 0));
+    if (int rc = render_enqueue(*sc, p, (float*)dbuf, cnt, run)) return rc;
+    CU_TRY(cudaEventRecord(pipe.evRender[slot], sc->stream));
+    // HBM -> host, batch by batch when a callback wants the reference's batch granularity
+    CU_TRY(cudaStreamWaitEvent(pipe.out, pipe.evRender[slot], 0));
+    CU_TRY(timing_event(pipe.out));
+    if (!cb && stride == 1) {
+      CU_TRY(cudaMemcpyAsync((char*)rays + batch_lo(j0) * 84, dbuf, cnt * 84, cudaMemcpyDeviceToHost, pipe.out));
+    } else {
+      for (size_t j = j0; j < j1; ++j) {
+        char* hb = (char*)rays + batch_lo(j) * 84;
+        CU_TRY(cudaMemcpyAsync(hb, dbuf + (j - j0) * batch * 84, batch_len(j) * 84, cudaMemcpyDeviceToHost, pipe.out));
+        if (cb) {
+          jobs[j] = CallbackJob{cb, user, firstBatch + j * stride, hb, batch_len(j)};  // k * R + replica, RayCallback.cpp:8-24
+          CU_TRY(cudaLaunchHostFunc(pipe.out, run_callback_job, &jobs[j]));
+        }
+      }
+    }
+    CU_TRY(timing_event(pipe.out));
+    CU_TRY(cudaEventRecord(pipe.evOut[slot], pipe.out));
   }
-  CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-  sc->stats.d2h_ms = ms;
+  CU_TRY(cudaStreamSynchronize(pipe.out));
+  if (int rc = render_end(*sc, run)) return rc;
+  sc->stats.trace_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  // copy time = sum over tiles (the copies of different tiles overlap the kernels, not each other)
+  for (size_t i = 0; i + 4 <= pipe.timing.size(); i += 4) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pipe.timing[i], pipe.timing[i + 1]) == cudaSuccess) sc->stats.h2d_ms += ms;
+    if (cudaEventElapsedTime(&ms, pipe.timing[i + 2], pipe.timing[i + 3]) == cudaSuccess) sc->stats.d2h_ms += ms;
+  }
   return B200RT_OK;
 }
 

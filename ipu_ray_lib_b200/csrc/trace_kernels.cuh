@@ -11,6 +11,7 @@
 // stay busy through the bounce loop regardless of path length, while rgb is still accumulated in
 // sample order (bit-identical to the sequential reference loop).
 #pragma once
+#include "async_copy.cuh"
 #include "rt_device.cuh"
 
 namespace rt {
@@ -185,6 +186,169 @@ __global__ void __launch_bounds__(768) shadow_trace_kernel(const TraceArgs a) {
       tr[TR_IDS] = __uint_as_float(ids | (kFlagEscaped << 16));
     }
   }
+  flush_counters(a.counters, nClosest, nOccl, cnt, 0u, 0u);
+}
+
+// -------------------------------------------------------------------------------------------------
+// shadow_stream_kernel: the same single-pass render with the ray stream moved by the TMA engine.
+//
+// The caller's TraceResult stream is AoS, 84 B per ray. A tile = 32 consecutive rays = 2688 contiguous, 16-byte
+// aligned bytes, which is exactly what a 1-D bulk copy moves. Per persistent CTA (one per SM, the pair table staged in
+// shared memory beside the rings):
+//   * warp 0 is the PRODUCER: it claims tile ids from the global counter and keeps a ring of kLoadSlots tiles in flight
+//     with cp.async.bulk global -> shared, each completing on the slot's mbarrier (the ring is the multi-buffering: up
+//     to 8 tiles = 21 KB per SM are on their way while the other warps trace);
+//   * warps 1..23 are CONSUMERS: each takes the next landed tile, every lane copies ITS ray's 21 words out of the slot
+//     (word stride 21 is odd: conflict-free; this is the AoS -> per-lane "SoA in registers" transposition), the slot
+//     goes straight back to the producer, the warp traces its 32 rays (closest hit + shadow ray), writes the 32 finished
+//     records into a store slot and one lane sends it home with cp.async.bulk shared -> global.
+// HBM therefore sees only full, aligned 2688-byte bursts in both directions, issued asynchronously to the traversal,
+// instead of 21 strided word loads and 13 strided word stores per lane.
+constexpr int kStreamTileRays = 32;
+constexpr uint32_t kStreamTileBytes = kStreamTileRays * TR_WORDS * 4u;  // 2688
+constexpr int kLoadSlots = 8, kStoreSlots = 6;
+constexpr int kStreamThreads = 768;
+constexpr uint32_t kStreamNoTile = 0xFFFFFFFFu;
+struct StreamCtl {
+  uint64_t full[kLoadSlots];    // tile landed (transaction bytes)
+  uint64_t empty[kLoadSlots];   // tile copied into registers by its consumer
+  uint32_t tileOf[kLoadSlots];  // tile id held by the slot, kStreamNoTile = end of stream
+  uint32_t storeGen[kStoreSlots];  // completed uses of each store slot
+  uint32_t published;           // load tickets the producer has issued
+  uint32_t loadTicket, storeTicket;
+};
+constexpr uint32_t kStreamRingBytes = (kLoadSlots + kStoreSlots) * kStreamTileBytes + 256u;
+static_assert(sizeof(StreamCtl) <= 256, "control block");
+
+template <bool kShared, bool kCount>
+__global__ void __launch_bounds__(kStreamThreads) shadow_stream_kernel(const TraceArgs a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const uint32_t pairBytes = kShared ? a.scene.numPairs * 48u : 0u;
+  unsigned char* loadRing = smemRaw + pairBytes;
+  unsigned char* storeRing = loadRing + kLoadSlots * kStreamTileBytes;
+  StreamCtl* ctl = reinterpret_cast<StreamCtl*>(storeRing + kStoreSlots * kStreamTileBytes);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kLoadSlots; ++i) { ac::mbar_init(&ctl->full[i], 1); ac::mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < kStoreSlots; ++i) ctl->storeGen[i] = 0u;
+    ctl->published = 0u; ctl->loadTicket = 0u; ctl->storeTicket = 0u;
+    ac::fence_barrier_init();
+  }
+  const uint4* pairs = stage_pairs<kShared>(a, reinterpret_cast<uint4*>(smemRaw));
+  __syncthreads();
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t numTiles = (a.numRays + kStreamTileRays - 1) / kStreamTileRays;
+  const uint32_t numConsumers = (blockDim.x >> 5) - 1u;
+  Counters cnt = {0u, 0u};
+  unsigned nClosest = 0, nOccl = 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ticket = 0;
+      auto publish = [&](uint32_t t) {
+        const uint32_t slot = ticket % kLoadSlots, phase = (ticket / kLoadSlots) & 1u;
+        ac::mbar_wait(&ctl->empty[slot], phase ^ 1u);  // the slot's previous tile has been taken
+        ctl->tileOf[slot] = t;
+        const bool whole = t != kStreamNoTile && (size_t)(t + 1u) * kStreamTileRays <= a.numRays;
+        if (whole) {
+          ac::mbar_expect_tx(&ctl->full[slot], kStreamTileBytes);
+          ac::bulk_load(loadRing + slot * kStreamTileBytes, a.rays + (size_t)t * kStreamTileRays * TR_WORDS, kStreamTileBytes,
+                        &ctl->full[slot]);
+        } else {
+          ac::mbar_arrive(&ctl->full[slot]);  // end marker, or the ragged last tile (read with plain loads)
+        }
+        ++ticket;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t*>(&ctl->published) = ticket;
+      };
+      while (true) {
+        const uint32_t base = atomicAdd(a.workCounter, 4u);
+        if (base >= numTiles) break;
+        const uint32_t end = min(base + 4u, numTiles);
+        for (uint32_t t = base; t < end; ++t) publish(t);
+      }
+      for (uint32_t c = 0; c < numConsumers; ++c) publish(kStreamNoTile);
+    }
+  } else {
+    bool stored = false;
+    while (true) {
+      uint32_t ticket = 0;
+      if (lane == 0) ticket = atomicAdd(&ctl->loadTicket, 1u);
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      const uint32_t slot = ticket % kLoadSlots, phase = (ticket / kLoadSlots) & 1u;
+      // only wait on the slot's barrier once OUR ticket is the one in flight there (a parity bit cannot tell the phases
+      // of tickets k and k + 2 * kLoadSlots apart, and more consumers than slots may be queueing)
+      while (*reinterpret_cast<volatile uint32_t*>(&ctl->published) <= ticket) __nanosleep(32);
+      ac::mbar_wait(&ctl->full[slot], phase);
+      const uint32_t tile = ctl->tileOf[slot];
+      if (tile == kStreamNoTile) {
+        __syncwarp();
+        if (lane == 0) ac::mbar_arrive(&ctl->empty[slot]);
+        break;
+      }
+      const uint32_t first = tile * kStreamTileRays;
+      const uint32_t inTile = min((uint32_t)kStreamTileRays, a.numRays - first);
+      const bool whole = inTile == kStreamTileRays;
+      const bool mine = lane < inTile;
+      float w[TR_WORDS];
+      if (whole) {
+        const float* src = reinterpret_cast<const float*>(loadRing + slot * kStreamTileBytes) + lane * TR_WORDS;
+#pragma unroll
+        for (int i = 0; i < TR_WORDS; ++i) w[i] = src[i];
+      } else {
+        const float* src = a.rays + (size_t)(first + (mine ? lane : 0u)) * TR_WORDS;
+#pragma unroll
+        for (int i = 0; i < TR_WORDS; ++i) w[i] = src[i];
+      }
+      __syncwarp();
+      if (lane == 0) ac::mbar_arrive(&ctl->empty[slot]);  // slot back to the producer before the tracing starts
+
+      if (mine) {
+        const V3 o = mk(w[TR_ORIGIN], w[TR_ORIGIN + 1], w[TR_ORIGIN + 2]);
+        const V3 d = mk(w[TR_DIR], w[TR_DIR + 1], w[TR_DIR + 2]);
+        nClosest++;
+        const ShadowOut r = shadow_one<kShared, true, kCount>(a, pairs, o, d, w[TR_TMIN], w[TR_TMAX], cnt, nOccl);
+        const uint32_t ids = __float_as_uint(w[TR_IDS]);
+        if (r.hit) {
+          w[TR_RGB] = r.color.x; w[TR_RGB + 1] = r.color.y; w[TR_RGB + 2] = r.color.z;
+          w[TR_ORIGIN] = r.o.x; w[TR_ORIGIN + 1] = r.o.y; w[TR_ORIGIN + 2] = r.o.z;
+          w[TR_TMAX] = r.t;
+          w[TR_PRIM] = __uint_as_float(r.primID);
+          w[TR_NORMAL] = r.n.x; w[TR_NORMAL + 1] = r.n.y; w[TR_NORMAL + 2] = r.n.z;
+          w[TR_IDS] = __uint_as_float((ids & 0xffff0000u) | r.geomID);
+        } else {
+          w[TR_IDS] = __uint_as_float(ids | (kFlagEscaped << 16));
+        }
+      }
+      __syncwarp();
+      if (whole) {
+        uint32_t st = 0;
+        if (lane == 0) st = atomicAdd(&ctl->storeTicket, 1u);
+        st = __shfl_sync(0xffffffffu, st, 0);
+        const uint32_t sslot = st % kStoreSlots, gen = st / kStoreSlots;
+        // the slot's previous bulk store must have finished reading it
+        while (*reinterpret_cast<volatile uint32_t*>(&ctl->storeGen[sslot]) != gen) __nanosleep(32);
+        float* dst = reinterpret_cast<float*>(storeRing + sslot * kStreamTileBytes) + lane * TR_WORDS;
+#pragma unroll
+        for (int i = 0; i < TR_WORDS; ++i) dst[i] = w[i];
+        ac::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ac::bulk_store(a.rays + (size_t)first * TR_WORDS, storeRing + sslot * kStreamTileBytes, kStreamTileBytes);
+          ac::bulk_commit();
+          ac::bulk_wait_read_all();
+          __threadfence_block();
+          *reinterpret_cast<volatile uint32_t*>(&ctl->storeGen[sslot]) = gen + 1u;
+          stored = true;
+        }
+      } else if (mine) {
+        float* dst = a.rays + (size_t)(first + lane) * TR_WORDS;
+#pragma unroll
+        for (int i = 0; i < TR_WORDS; ++i) dst[i] = w[i];
+      }
+    }
+    if (stored) ac::bulk_wait_all();  // this lane's bulk stores have reached global memory
+  }
+  __syncwarp();
   flush_counters(a.counters, nClosest, nOccl, cnt, 0u, 0u);
 }
 

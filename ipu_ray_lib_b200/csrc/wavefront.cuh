@@ -34,6 +34,7 @@ struct WfBuffers {
   float4* hitA;       // [P] t, geomID bits, primID bits, tri bits
   float4* hitB;       // [P] b0, b1, b2; only when the scene interpolates normals (else null)
   uint32_t* queue[2];  // [P] path ids of the current / next bounce
+  const uint32_t* traceOrder;  // optional: the current queue's path ids in the order wf_trace should take them (null = queue order)
   uint32_t* counts;   // [0],[1] queue sizes, [2] fetch cursor of wf_trace
 };
 
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
   const float inf = __int_as_float(0x7f800000);
   // bounce 0 (kFirst): the queue is the identity over all paths of the chunk and the rays are the camera rays
-  const uint32_t* queue = a.b.queue[a.qIn];
+  const uint32_t* queue = a.b.traceOrder ? a.b.traceOrder : a.b.queue[a.qIn];
   const uint32_t count = kFirst ? a.numPaths : a.b.counts[a.qIn];
   uint32_t* cursor = a.b.counts + 2;
   Counters cnt = {0u, 0u};
@@ -446,5 +447,28 @@ __global__ void __launch_bounds__(256) wf_accumulate_kernel(float* rays, uint32_
   }
   if (threadIdx.x < pixels) { tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z; }
 }
+
+#ifdef B200RT_EXPERIMENT_SORT
+// EXPERIMENT (make experiments): sort key of every queued path = (origin cell 5 bits per axis | octahedral direction
+// bin 3 + 3 bits), to measure how much ray coherence is worth to wf_trace. Entries past the queue's end get the
+// largest key.
+__global__ void wf_sort_key_kernel(const WfArgs a, uint32_t* keys, uint32_t* ids, float3 boxMin, float3 boxInvExt) {
+  const uint32_t count = a.b.counts[a.qIn];
+  const uint32_t* queue = a.b.queue[a.qIn];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.numPaths; i += gridDim.x * blockDim.x) {
+    if (i >= count) { keys[i] = 0xFFFFFFFFu; ids[i] = 0u; continue; }
+    const uint32_t p = queue[i];
+    const float4 ro = a.b.rayO[p], rd = a.b.rayD[p];
+    auto cell = [](float x, float mn, float inv) { const int c = (int)((x - mn) * inv * 32.f); return (uint32_t)min(max(c, 0), 31); };
+    const uint32_t cx = cell(ro.x, boxMin.x, boxInvExt.x), cy = cell(ro.y, boxMin.y, boxInvExt.y), cz = cell(ro.z, boxMin.z, boxInvExt.z);
+    const float n1 = fabsf(rd.x) + fabsf(rd.y) + fabsf(rd.z);
+    float u = rd.x / n1, v = rd.y / n1;
+    if (rd.z < 0.f) { const float uu = (1.f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f), vv = (1.f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f); u = uu; v = vv; }
+    const uint32_t du = (uint32_t)min(max((int)((u * .5f + .5f) * 8.f), 0), 7), dv = (uint32_t)min(max((int)((v * .5f + .5f) * 8.f), 0), 7);
+    keys[i] = (((cz << 10) | (cy << 5) | cx) << 6) | (dv << 3) | du;
+    ids[i] = p;
+  }
+}
+#endif
 
 }  // namespace rt

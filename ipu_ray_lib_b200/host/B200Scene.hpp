@@ -155,17 +155,15 @@ class B200Scene {
     return d;
   }
 
-  struct CallbackCtx {
-    B200Scene* self;
-    std::size_t replica, numReplicas;
-  };
-  static void trampoline(std::size_t localIndex, const void* rays, std::size_t n, void* user) {
-    auto* ctx = (CallbackCtx*)user;
-    const std::size_t batchIndex = localIndex * ctx->numReplicas + ctx->replica;  // RayCallback::fetch numbering
-    auto& batch = ctx->self->rayBatches_[batchIndex];
+  // batchIndex is the batch's index in the whole stream = k * numReplicas + replica, the numbering of
+  // RayCallback::fetch (src/RayCallback.cpp:8-24). Runs on a CUDA-owned host thread of that replica; replicas may call
+  // concurrently (as the reference's per-replica stream callbacks do), each on its own rayBatches_ entry.
+  static void trampoline(std::size_t batchIndex, const void* rays, std::size_t n, void* user) {
+    auto* self = (B200Scene*)user;
+    auto& batch = self->rayBatches_[batchIndex];
     batch.resize(n);
     std::memcpy(batch.data(), rays, n * sizeof(TraceResult));
-    (*ctx->self->rayFunc_)(batchIndex, batch);
+    (*self->rayFunc_)(batchIndex, batch);
   }
 
   void execute() {
@@ -179,27 +177,18 @@ class B200Scene {
     rayBatches_.assign(numBatches, {});
     if (rayFunc_)
       for (std::size_t b = 0; b < numBatches; ++b) rayBatches_[b].resize(std::min(rayStream_.size(), (b + 1) * per) - b * per);
-    // One replica renders the caller's stream in place. Several replicas each get the batches i % R
-    // (src/IpuScene.cpp:676-684) gathered into one contiguous stream, so that every GPU is filled by a single trace.
-    std::vector<std::vector<TraceResult>> perReplica(R > 1 ? R : 0);
-    if (R > 1)
-      for (std::size_t b = 0; b < numBatches; ++b) {
-        const std::size_t lo = b * per, hi = std::min(rayStream_.size(), lo + per);
-        perReplica[b % R].insert(perReplica[b % R].end(), rayStream_.begin() + (long)lo, rayStream_.begin() + (long)hi);
-      }
-    auto streamOf = [&](std::size_t r) -> std::vector<TraceResult>& { return R > 1 ? perReplica[r] : rayStream_; };
-
+    // Every replica renders ITS batches (i % R == replica, src/IpuScene.cpp:676-684) of the caller's stream in place:
+    // b200rt_trace takes the stride, so the stream is neither regrouped nor copied on the host.
     // Phase 1 (untimed, like the reference's compile/load/prepareEngine): device scenes, NIF weights, page-locking.
     std::vector<std::string> errors(R);
     std::vector<b200rt_scene*> scenes(R, nullptr);
-    std::vector<char> pinned(R, 0);
     auto forEachReplica = [&](auto&& body) {
       std::vector<std::thread> threads;
       for (std::size_t r = 0; r < R; ++r) threads.emplace_back([&, r] { body(r); });
       for (auto& t : threads) t.join();
     };
     forEachReplica([&](std::size_t r) {
-      const b200rt_scene_desc d = makeDesc((int)r);
+      const b200rt_scene_desc d = makeDesc(b200rt_device_ordinal((int)r));  // r-th usable (sm_100) device, not raw ordinal r
       if (b200rt_scene_create(&d, &scenes[r]) != 0) { errors[r] = b200rt_last_error(); return; }
       if (haveNif_ && data_.pathTrace) {
         std::vector<b200rt_nif_layer> layers(nif_.layers.size());
@@ -216,42 +205,32 @@ class B200Scene {
         b200rt_scene_set_hdri_rotation(scenes[r], hdriRotationDegrees_);
         b200rt_scene_set_max_nif_batch_size(scenes[r], nifMaxRaysPerBatch_);
       }
-      auto& stream = streamOf(r);
-      if (!stream.empty()) pinned[r] = b200rt_host_register(stream.data(), stream.size() * sizeof(TraceResult)) == 0;
     });
+    // page-lock the shared stream once (portable: every device DMA's from it)
+    const bool pinnedStream = !rayStream_.empty() &&
+                              b200rt_host_register(rayStream_.data(), rayStream_.size() * sizeof(TraceResult)) == 0;
 
     // Phase 2 (timed; the span of IpuScene::getTraceTimeSecs, src/IpuScene.cpp:672-696): stream in, trace, stream out.
     std::vector<b200rt_trace_stats> stats(R);
     const auto t0 = std::chrono::steady_clock::now();
     forEachReplica([&](std::size_t r) {
-      auto& stream = streamOf(r);
-      if (!errors[r].empty() || stream.empty()) return;
+      if (!errors[r].empty() || rayStream_.empty() || r >= numBatches) return;
       b200rt_trace_params p{};
       p.rays_per_batch = (std::uint32_t)per;
-      CallbackCtx ctx{this, r, R};
-      if (b200rt_trace(scenes[r], &p, stream.data(), stream.size(), rayFunc_ ? &B200Scene::trampoline : nullptr, &ctx) != 0)
+      p.batch_stride = (std::uint32_t)R;
+      p.first_batch = (std::uint32_t)r;
+      if (b200rt_trace(scenes[r], &p, rayStream_.data(), rayStream_.size(), rayFunc_ ? &B200Scene::trampoline : nullptr, this) != 0)
         errors[r] = b200rt_last_error();
       b200rt_get_trace_stats(scenes[r], &stats[r]);
     });
     traceTimeSecs_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
-    for (std::size_t r = 0; r < R; ++r) {
-      if (pinned[r]) b200rt_host_unregister(streamOf(r).data());
+    if (pinnedStream) b200rt_host_unregister(rayStream_.data());
+    for (std::size_t r = 0; r < R; ++r)
       if (scenes[r]) b200rt_scene_destroy(scenes[r]);
-    }
     for (auto& e : errors)
       if (!e.empty()) throw std::runtime_error(e);
 
-    // un-batch into the caller's stream (src/IpuScene.cpp:715-732)
-    if (R > 1) {
-      std::vector<std::size_t> cursor(R, 0);
-      for (std::size_t b = 0; b < numBatches; ++b) {
-        const std::size_t r = b % R, n = std::min(rayStream_.size(), (b + 1) * per) - b * per;
-        std::copy(perReplica[r].begin() + (long)cursor[r], perReplica[r].begin() + (long)(cursor[r] + n),
-                  rayStream_.begin() + (long)(b * per));
-        cursor[r] += n;
-      }
-    }
     stats_ = b200rt_trace_stats{};
     for (auto& s : stats) {
       stats_.closest_hit_queries += s.closest_hit_queries; stats_.occlusion_queries += s.occlusion_queries;

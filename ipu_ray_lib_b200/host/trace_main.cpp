@@ -25,7 +25,7 @@ namespace {
 
 struct Options {
   std::string outprefix = "out", crop, meshFile, nifHdri, scene = "box", visualise = "rgb", renderMode = "path-trace",
-              logLevel = "info";
+              logLevel = "info", saveRayStream, builtinMesh = "../assets/monkey_bust.glb";
   std::uint32_t ipus = 4, maxPathLength = 10, rouletteStartDepth = 3, samples = 256;
   std::size_t raysPerWorker = 1, maxNifBatchSize = 0;
   std::int32_t width = 768, height = 432;
@@ -47,6 +47,8 @@ const char* kHelp =
     "  --mesh-file arg                 Scene file (.dae / .glb with a camera). Default: built-in scene.\n"
     "  --nif-hdri arg                  Path to the 'assets.extra' directory of a NIF model.\n"
     "  --nif-synthetic                 (extension) use fixed-seed synthetic NIF weights shaped by the metadata.\n"
+    "  --save-ray-stream arg           (extension) write the raw TraceResult stream (rgb = sum over samples) to a file.\n"
+    "  --builtin-mesh arg              (extension) mesh placed in the built-in box scene (=../assets/monkey_bust.glb).\n"
     "  --hdri-rotation arg (=0)        Azimuthal rotation for HDRI environment map (degrees).\n"
     "  --load-normals                  Load and interpolate mesh normals from --mesh-file.\n"
     "  --scene arg (=box)              One of [box-simple, box, spheres].\n"
@@ -102,6 +104,8 @@ Options parse(int argc, char** argv) {
     else if (a == "--mesh-file") o.meshFile = val();
     else if (a == "--nif-hdri") o.nifHdri = val();
     else if (a == "--nif-synthetic") o.nifSynthetic = true;
+    else if (a == "--save-ray-stream") o.saveRayStream = val();
+    else if (a == "--builtin-mesh") o.builtinMesh = val();
     else if (a == "--hdri-rotation") o.hdriRotation = std::stof(val());
     else if (a == "--load-normals") o.loadNormals = true;
     else if (a == "--scene") o.scene = val();
@@ -187,7 +191,7 @@ int main(int argc, char** argv) {
     // ===== Scene setup (buildSceneDescription + buildSceneData) =====
     SceneParts parts;
     if (args.meshFile.empty()) {
-      if (args.scene == "box" || args.scene == "box-simple") parts = makeCornellBoxScene("../assets/monkey_bust.glb", args.scene == "box-simple");
+      if (args.scene == "box" || args.scene == "box-simple") parts = makeCornellBoxScene(args.builtinMesh, args.scene == "box-simple");
       else if (args.scene == "spheres") parts = makePrimitiveScene();
       else throw std::runtime_error("Invalid scene selection: '" + args.scene + "'");
     } else {
@@ -240,6 +244,12 @@ int main(int argc, char** argv) {
     LOG("info", "B200 Rendering started.");
     if (device.run() != EXIT_SUCCESS) return EXIT_FAILURE;
     LOG("info", "B200 Rendering finished.");
+    if (!args.saveRayStream.empty()) {
+      FILE* f = std::fopen(args.saveRayStream.c_str(), "wb");
+      if (!f || std::fwrite(rayStream.data(), sizeof(TraceResult), rayStream.size(), f) != rayStream.size())
+        throw std::runtime_error("could not write " + args.saveRayStream);
+      std::fclose(f);
+    }
     if (pathTrace) b200rt_scale_rgb(rayStream.data(), rayStream.size(), 1.f / (float)args.samples);
 
     const double secs = device.getTraceTimeSecs();

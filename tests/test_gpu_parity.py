@@ -397,3 +397,66 @@ def test_error_flag_on_unknown_material(B200Scene, port):
     a["rgb"][err] = 0
     b["rgb"][err] = 0
     assert_streams_identical(a, b, "error flag")
+
+
+@pytest.mark.parametrize("w,h", [(131, 97), (7, 3), (1, 1), (257, 129)])
+def test_shadow_stream_ragged_tiles(B200Scene, port, box_scene, w, h):
+    """The TMA-staged single-pass kernel moves 32-ray tiles; streams that end in a partial tile (or are shorter than one
+    tile) take the plain-load tail path."""
+    s = box_scene.configure(w, h, path_trace=False)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    cw = port.shadow_trace(s, want)
+    with B200Scene(s) as g:
+        for res in (1, 2):
+            got = base.copy()
+            g.execute(got, scene_residency=res)
+            assert_streams_identical(got, want, f"shadow stream {w}x{h} res={res}")
+            assert g.stats()["occlusion_queries"] == cw["occlusion_queries"]
+
+
+def test_host_streaming_pipeline_many_tiles(B200Scene, port, box_scene):
+    """b200rt_trace streams the host-resident stream through three device tile buffers (H2D || kernels || D2H). Small
+    batches force dozens of tiles; callbacks arrive from a CUDA-owned host thread, once per batch, in order, each seeing
+    finished rays; strided batch lists (replica r of R) touch exactly their batches."""
+    import threading
+
+    w, h = 640, 480
+    s = box_scene.configure(w, h, path_trace=False)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    port.shadow_trace(s, want)
+    seen, threads = [], set()
+
+    def cb(idx, batch):
+        threads.add(threading.get_ident())
+        seen.append((idx, batch.copy()))
+
+    with B200Scene(s, ray_callback=cb) as g:
+        got = base.copy()
+        g.execute(got, rays_per_batch=70000)  # wantTile 2^17 -> 1 batch per tile, 5 tiles over the 3-slot ring
+        assert_streams_identical(got, want, "pipelined shadow")
+        assert [i for i, _ in seen] == list(range((w * h + 69999) // 70000))
+        assert_streams_identical(np.concatenate([b for _, b in seen]), want, "callback batches")
+        assert threading.get_ident() not in threads  # invoked on a library/CUDA-owned thread, not the caller's
+        st = g.stats()
+        assert st["h2d_ms"] > 0 and st["d2h_ms"] > 0
+    with B200Scene(s) as g:
+        # two "replicas" sharing one host stream: batches 0,2,4.. then 1,3,5.. rendered in place
+        got = base.copy()
+        g.execute(got, rays_per_batch=8640, batch_stride=2, first_batch=0)
+        owner = (np.arange(w * h) // 8640) % 2
+        assert_streams_identical(got[owner == 0], want[owner == 0], "replica 0 batches")
+        assert_streams_identical(got[owner == 1], base[owner == 1], "replica 1 batches untouched")
+        g.execute(got, rays_per_batch=8640, batch_stride=2, first_batch=1)
+        assert_streams_identical(got, want, "both replicas")
+    # path tracing through the same pipeline (tiles of ~1 M rays: two tiles here)
+    w, h, spp = 1200, 1000, 2
+    s = box_scene.configure(w, h, path_trace=True, samples=spp, seed=77)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    port.path_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got)
+        assert_streams_identical(got, want, "pipelined path trace")
