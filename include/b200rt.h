@@ -172,7 +172,8 @@ typedef struct b200rt_nif_desc {
 int b200rt_scene_load_nif(b200rt_scene* scene, const b200rt_nif_desc* nif);
 /* IpuScene::setHdriRotation (src/IpuScene.cpp:334-336), degrees. */
 int b200rt_scene_set_hdri_rotation(b200rt_scene* scene, float degrees);
-/* IpuScene::setMaxNifBatchSize (src/IpuScene.cpp:342-344); 0 = auto. */
+/* IpuScene::setMaxNifBatchSize (src/IpuScene.cpp:342-344, used at :265-327): the escaped rays of a chunk are looked up
+ * in serial NIF launches of at most this many rays; 0 = auto (one launch per chunk). Results do not depend on it. */
 int b200rt_scene_set_max_nif_batch_size(b200rt_scene* scene, size_t rays_per_batch);
 /* Stand-alone NIF evaluation of n (u,v) pairs -> n bgr triples (fp32), for parity tests:
  * the encode + MLP + decode of src/neural_networks/NifModel.cpp:186-246,296-327.

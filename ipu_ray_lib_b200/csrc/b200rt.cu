@@ -500,7 +500,8 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
           timer.begin(KernelTimer::NIF, sc.stream);
           const int rc = rt::nif_eval_queue(sc.nif, (const float*)sc.slotEscape.p, (const uint32_t*)sc.escapeQueue.p,
                                             (const uint32_t*)sc.escapeCount.p, (uint32_t)std::min<size_t>((size_t)c * n, 0xFFFFFFFFull),
-                                            (float*)sc.slotEnv.p, sc.stream, &nifLaunches);
+                                            (uint32_t)std::min<size_t>(sc.maxNifBatch, 0xFFFFFFFFull), (float*)sc.slotEnv.p, sc.stream,
+                                            &nifLaunches);
           timer.end(sc.stream);
           if (rc != 0) return fail(B200RT_ERR_CUDA, std::string("NIF evaluation failed: ") + rt::nif_last_error());
           launches += (uint64_t)nifLaunches;

@@ -16,6 +16,7 @@
 
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -79,15 +80,21 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
   t = tc::Params{};
   t.numLayers = (int)d.num_layers;
   t.embed = E;
-  int width = F, maxHidden = 16, prevN0 = 0;
-  std::vector<int> actRows(d.num_layers), featRows(d.num_layers);
+  int width = F, widthPad = F, maxHidden = 16, prevN0 = 0;
+  // actRows = K rows read from the (padded) activation planes; realActRows = how many of them carry real weights
+  std::vector<int> actRows(d.num_layers), featRows(d.num_layers), realActRows(d.num_layers);
   for (uint32_t i = 0; i < d.num_layers; ++i) {
     const b200rt_nif_layer& L = d.layers[i];
     tc::Layer& o = t.layers[i];
     const int K = (int)L.in_features;
-    o.N = (int)L.out_features; o.Npad = (o.N + 15) / 16 * 16; o.relu = L.relu;
+    o.N = (int)L.out_features; o.relu = L.relu;
     const bool last = i + 1 == d.num_layers;
-    if (!last && o.N != tc::kHalfN && o.N != 2 * tc::kHalfN) return no("hidden width is not 160 or 320");
+    // The layer pipeline is built for column halves of exactly kHalfN accumulator columns. Any hidden width up to
+    // 2 * kHalfN runs on it zero-padded to 160 or 320 columns: padded weight columns (and their bias entries) are zero, so
+    // the padded activations are relu(0) = 0, and the K rows of the next layer that would multiply them are zero too --
+    // every real output is the same sum of the same products (fp32 accumulation of exact zeros changes nothing).
+    if (!last && o.N > 2 * tc::kHalfN) return no("hidden layer wider than 320");
+    o.Npad = last ? (o.N + 15) / 16 * 16 : (o.N <= tc::kHalfN ? tc::kHalfN : 2 * tc::kHalfN);
     if (last && o.Npad > tc::kHalfN) return no("output layer wider than one accumulator slot");
     o.n0 = std::min(o.Npad, tc::kHalfN);
     o.n1 = o.Npad - o.n0;
@@ -95,18 +102,20 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
       if (K != F) return no("first layer does not take the encoded input");
       actRows[i] = 0; featRows[i] = F;
     } else if (K == width + F) {  // skip-concat (NifModel.cpp:303-309)
-      actRows[i] = width; featRows[i] = F;
+      actRows[i] = widthPad; featRows[i] = F;
     } else if (K == width) {
-      actRows[i] = width; featRows[i] = 0;
+      actRows[i] = widthPad; featRows[i] = 0;
     } else {
       return no("layer input width mismatch");
     }
+    realActRows[i] = i == 0 ? 0 : width;
     o.actLoSlices = std::min(actRows[i], prevN0) / 16;
     o.actHiSlices = actRows[i] / 16 - o.actLoSlices;
     o.staticSlices = 1 + featRows[i] / 16;
     width = o.N;
+    widthPad = o.Npad;
     prevN0 = o.n0;
-    if (!last) maxHidden = std::max(maxHidden, o.N);
+    if (!last) maxHidden = std::max(maxHidden, o.Npad);
   }
   if (width != 3) return no("last layer must have 3 outputs");
   t.actPlanes = maxHidden / 8;
@@ -134,13 +143,16 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
         for (int n = 0; n < nCols; ++n)
           if (nBase + n < o.N) img[at + ((size_t)(k / 8) * nCols + n) * 8 + (k % 8)] = value(k, nBase + n);
     };
+    const int realAct = realActRows[i];  // activation rows beyond this are padding (zero weights)
     auto loValue = [&](int k, int n) -> __half {
-      if (k < loAct) return src[(size_t)k * o.N + n];
+      if (k < loAct) return k < realAct ? src[(size_t)k * o.N + n] : __float2half(0.f);
       if (k == loAct) return bias ? bias[n] : __float2half(0.f);
       if (k < loAct + 16) return __float2half(0.f);
-      return src[(size_t)(actRows[i] + (k - loAct - 16)) * o.N + n];  // encoded-input rows follow the activation rows
+      return src[(size_t)(realAct + (k - loAct - 16)) * o.N + n];  // encoded-input rows follow the activation rows
     };
-    auto hiValue = [&](int k, int n) -> __half { return src[(size_t)(loAct + k) * o.N + n]; };
+    auto hiValue = [&](int k, int n) -> __half {
+      return loAct + k < realAct ? src[(size_t)(loAct + k) * o.N + n] : __float2half(0.f);
+    };
     block(loK, 0, o.n0, loValue);
     if (o.n1) block(loK, o.n0, o.n1, loValue);
     if (hiAct) block(hiAct, 0, o.n0, hiValue);
@@ -249,12 +261,12 @@ __global__ void __launch_bounds__(kThreads) nif_mlp_kernel(const NifParams p, co
                                                            const float* __restrict__ slotEscape,
                                                            const uint32_t* __restrict__ queue,
                                                            const uint32_t* __restrict__ dCount, uint32_t directCount,
-                                                           float* __restrict__ out) {
+                                                           uint32_t first, float* __restrict__ out) {
   __shared__ __half actA[kTileRows][kMaxWidth + 64];
   __shared__ __half actB[kTileRows][kMaxWidth + 64];
   __shared__ __half feat[kTileRows][64];
   __shared__ uint32_t rowSlot[kTileRows];
-  const uint32_t count = uvDirect ? directCount : min(*dCount, directCount);
+  const uint32_t count = uvDirect ? directCount : min(*dCount > first ? *dCount - first : 0u, directCount);
   const int F = 4 * p.embed;
   for (uint32_t tile = blockIdx.x; (uint64_t)tile * kTileRows < count; tile += gridDim.x) {
     const uint32_t row0 = tile * kTileRows;
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(kThreads) nif_mlp_kernel(const NifParams p, co
 }  // namespace
 
 static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, const uint32_t* queue,
-                  const uint32_t* dCount, uint32_t count, float* out, cudaStream_t stream, int* launches) {
+                  const uint32_t* dCount, uint32_t count, uint32_t first, float* out, cudaStream_t stream, int* launches) {
   if (!m) { g_nifError = "no model"; return -1; }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
@@ -334,7 +346,7 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
       cudaMemsetAsync(dProf, 0, (size_t)tcGrid * 16 * sizeof(unsigned long long), stream);
       params.prof = dProf;
     }
-    tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(params, uvDirect, slotEscape, queue, dCount, count, out);
+    tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(params, uvDirect, slotEscape, queue, dCount, count, first, out);
     const cudaError_t te = cudaGetLastError();
     if (te != cudaSuccess) { g_nifError = cudaGetErrorString(te); return -1; }
     if (profile) {  // debugging aid: per-role cycle breakdown of CTA 0 (synchronises!)
@@ -354,7 +366,7 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
   }
   const uint32_t tiles = (count + kTileRows - 1) / kTileRows;
   const uint32_t grid = tiles < (uint32_t)(sms * 4) ? (tiles ? tiles : 1u) : (uint32_t)(sms * 4);
-  nif_mlp_kernel<<<grid, kThreads, 0, stream>>>(m->p, uvDirect, slotEscape, queue, dCount, count, out);
+  nif_mlp_kernel<<<grid, kThreads, 0, stream>>>(m->p, uvDirect, slotEscape, queue, dCount, count, first, out);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_nifError = cudaGetErrorString(e); return -1; }
   if (launches) *launches += 1;
@@ -362,12 +374,19 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
 }
 
 int nif_eval_uv(NifModel* m, const float* dUv, uint32_t n, float* dBgrOut, cudaStream_t stream, int* launches) {
-  return launch(m, dUv, nullptr, nullptr, nullptr, n, dBgrOut, stream, launches);
+  return launch(m, dUv, nullptr, nullptr, nullptr, n, 0u, dBgrOut, stream, launches);
 }
 
+// maxBatch = IpuScene::setMaxNifBatchSize (src/IpuScene.cpp:265-327, :342-344): the queue is evaluated in serial
+// launches of at most that many escaped rays (0 = one launch). The queue length lives on the device, so launches are
+// issued for the whole possible range and those past its end find nothing to do.
 int nif_eval_queue(NifModel* m, const float* slotEscape, const uint32_t* queue, const uint32_t* dCount,
-                   uint32_t maxCount, float* slotEnv, cudaStream_t stream, int* launches) {
-  return launch(m, nullptr, slotEscape, queue, dCount, maxCount, slotEnv, stream, launches);
+                   uint32_t maxCount, uint32_t maxBatch, float* slotEnv, cudaStream_t stream, int* launches) {
+  if (maxBatch == 0 || maxBatch >= maxCount) return launch(m, nullptr, slotEscape, queue, dCount, maxCount, 0u, slotEnv, stream, launches);
+  for (uint32_t first = 0; first < maxCount; first += maxBatch)
+    if (int rc = launch(m, nullptr, slotEscape, queue + first, dCount, std::min(maxBatch, maxCount - first), first, slotEnv, stream, launches))
+      return rc;
+  return 0;
 }
 
 }  // namespace rt

@@ -254,7 +254,7 @@ __device__ __forceinline__ void drain_to_regs(uint32_t taddr, bool relu, uint32_
 __global__ void __launch_bounds__(kThreads, 1)
 nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const float* __restrict__ slotEscape,
                   const uint32_t* __restrict__ queue, const uint32_t* __restrict__ dCount, uint32_t directCount,
-                  float* __restrict__ out) {
+                  uint32_t first, float* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // layout: [activation planes][static planes: ones, encoded input][ring stages][barriers][tmem ptr]
   unsigned char* X = smem;
@@ -273,7 +273,9 @@ nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const floa
   // the issuer's descriptors live in uniform registers instead of being re-broadcast per MMA
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t count = uvDirect ? directCount : min(*dCount, directCount);
+  // queue mode: this launch covers entries [first, first + directCount) of the device-side queue (`queue` already
+  // points at entry `first`); the queue's length is only known on the device
+  const uint32_t count = uvDirect ? directCount : min(*dCount > first ? *dCount - first : 0u, directCount);
   const uint32_t numTiles = (count + kRows - 1) / kRows;
 
   if (threadIdx.x == 0) {

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(768) shadow_trace_kernel(const TraceArgs a) {
 //   * warp 0 is the PRODUCER: it claims tile ids from the global counter and keeps a ring of kLoadSlots tiles in flight
 //     with cp.async.bulk global -> shared, each completing on the slot's mbarrier (the ring is the multi-buffering: up
 //     to 8 tiles = 21 KB per SM are on their way while the other warps trace);
-//   * warps 1..23 are CONSUMERS: each takes the next landed tile, every lane copies ITS ray's 21 words out of the slot
+//   * warps 1..24 are CONSUMERS: each takes the next landed tile, every lane copies ITS ray's 21 words out of the slot
 //     (word stride 21 is odd: conflict-free; this is the AoS -> per-lane "SoA in registers" transposition), the slot
 //     goes straight back to the producer, the warp traces its 32 rays (closest hit + shadow ray), writes the 32 finished
 //     records into a store slot and one lane sends it home with cp.async.bulk shared -> global.
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(768) shadow_trace_kernel(const TraceArgs a) {
 constexpr int kStreamTileRays = 32;
 constexpr uint32_t kStreamTileBytes = kStreamTileRays * TR_WORDS * 4u;  // 2688
 constexpr int kLoadSlots = 8, kStoreSlots = 6;
-constexpr int kStreamThreads = 768;
+constexpr int kStreamThreads = 800;  // 24 consumer warps + the producer warp (80 registers x 800 threads fit the file)
 constexpr uint32_t kStreamNoTile = 0xFFFFFFFFu;
 struct StreamCtl {
   uint64_t full[kLoadSlots];    // tile landed (transaction bytes)
@@ -270,6 +270,15 @@ __global__ void __launch_bounds__(kStreamThreads) shadow_stream_kernel(const Tra
     }
   } else {
     bool stored = false;
+    uint32_t pendingSlot = kStreamNoTile, pendingGen = 0;  // lane 0: store slot whose bulk store may still be reading it
+    auto retire_store = [&]() {
+      if (lane == 0 && pendingSlot != kStreamNoTile) {
+        ac::bulk_wait_read_all();
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t*>(&ctl->storeGen[pendingSlot]) = pendingGen + 1u;
+        pendingSlot = kStreamNoTile;
+      }
+    };
     while (true) {
       uint32_t ticket = 0;
       if (lane == 0) ticket = atomicAdd(&ctl->loadTicket, 1u);
@@ -283,6 +292,7 @@ __global__ void __launch_bounds__(kStreamThreads) shadow_stream_kernel(const Tra
       if (tile == kStreamNoTile) {
         __syncwarp();
         if (lane == 0) ac::mbar_arrive(&ctl->empty[slot]);
+        retire_store();
         break;
       }
       const uint32_t first = tile * kStreamTileRays;
@@ -301,6 +311,7 @@ __global__ void __launch_bounds__(kStreamThreads) shadow_stream_kernel(const Tra
       }
       __syncwarp();
       if (lane == 0) ac::mbar_arrive(&ctl->empty[slot]);  // slot back to the producer before the tracing starts
+      retire_store();  // the previous tile's bulk store has had the whole load phase to drain its slot
 
       if (mine) {
         const V3 o = mk(w[TR_ORIGIN], w[TR_ORIGIN + 1], w[TR_ORIGIN + 2]);
@@ -335,9 +346,7 @@ __global__ void __launch_bounds__(kStreamThreads) shadow_stream_kernel(const Tra
         if (lane == 0) {
           ac::bulk_store(a.rays + (size_t)first * TR_WORDS, storeRing + sslot * kStreamTileBytes, kStreamTileBytes);
           ac::bulk_commit();
-          ac::bulk_wait_read_all();
-          __threadfence_block();
-          *reinterpret_cast<volatile uint32_t*>(&ctl->storeGen[sslot]) = gen + 1u;
+          pendingSlot = sslot; pendingGen = gen;  // released once the copy has read the slot (retire_store)
           stored = true;
         }
       } else if (mine) {

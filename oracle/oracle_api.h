@@ -67,6 +67,10 @@ void ORC(camera_sample)(uint64_t rng_seed, uint32_t image_width, uint32_t image_
                         float anti_alias_scale, const uint32_t* row_col_sample /*[n][3]*/, size_t n, float* dirs_out);
 /* NIF forward for n (u,v) pairs -> bgr (port only; the reference has no CPU NIF). */
 int ORC(nif_eval)(const b200rt_nif_desc* nif, const float* uv, size_t n, float* bgr_out, int threads);
+/* Same with the IPU's matmul option partialsType = half modelled (src/IpuScene.cpp:256-262): the running sum is rounded
+ * to fp16 after every `half_chunk` products (0 = fp32 accumulation = nif_eval). Port only; a model, not a pinned
+ * restatement (poplibs' accumulation order is unpublished). */
+int ORC(nif_eval_partials)(const b200rt_nif_desc* nif, const float* uv, size_t n, float* bgr_out, int threads, int half_chunk);
 /* Equirect (u,v) of a direction (codelets/TraceCodelets.cpp:337-348); port only. */
 void ORC(dir_to_uv)(const float* dirs, size_t n, float rotation_radians, float* uv_out);
 

@@ -550,7 +550,11 @@ struct NifHost {
   }
 };
 
-void nifForward(const NifHost& host, float u, float v, float out[3]) {
+// halfChunk > 0 emulates the IPU's matmul option partialsType = half (src/IpuScene.cpp:256-262): products of
+// `halfChunk` consecutive k are summed exactly-ish (fp32, one AMP pass) and the running partial is ROUNDED TO FP16 after
+// every such group and again after the bias. poplibs does not publish its accumulation order, so this is a model of
+// that option, not a pinned restatement; it bounds how far fp16 partials can sit from the fp32-accumulate contract.
+void nifForward(const NifHost& host, float u, float v, float out[3], int halfChunk = 0) {
   const b200rt_nif_desc& nif = host.d;
   const int E = (int)nif.embedding_dimension, F = 4 * E;
   std::vector<float> feat((size_t)F);
@@ -571,10 +575,23 @@ void nifForward(const NifHost& host, float u, float v, float out[3]) {
     y.assign(L.out_features, 0.f);
     const float* W = host.w[l].data();
     // y[n] = sum_k x[k] * W[k][n], k ascending for every n (loop order chosen so the compiler vectorises over n)
-    for (uint32_t k = 0; k < L.in_features; ++k) {
-      const float xk = x[k];
-      const float* row = W + (size_t)k * L.out_features;
-      for (uint32_t n = 0; n < L.out_features; ++n) y[n] += xk * row[n];
+    if (halfChunk <= 0) {
+      for (uint32_t k = 0; k < L.in_features; ++k) {
+        const float xk = x[k];
+        const float* row = W + (size_t)k * L.out_features;
+        for (uint32_t n = 0; n < L.out_features; ++n) y[n] += xk * row[n];
+      }
+    } else {
+      std::vector<float> part(L.out_features);
+      for (uint32_t k0 = 0; k0 < L.in_features; k0 += (uint32_t)halfChunk) {
+        std::fill(part.begin(), part.end(), 0.f);
+        for (uint32_t k = k0; k < std::min<uint32_t>(L.in_features, k0 + (uint32_t)halfChunk); ++k) {
+          const float xk = x[k];
+          const float* row = W + (size_t)k * L.out_features;
+          for (uint32_t n = 0; n < L.out_features; ++n) part[n] += xk * row[n];
+        }
+        for (uint32_t n = 0; n < L.out_features; ++n) y[n] = halfToFloat(floatToHalf(y[n] + part[n]));
+      }
     }
     for (uint32_t n = 0; n < L.out_features; ++n) {
       float acc = y[n];
@@ -882,6 +899,13 @@ void orc_camera_sample(uint64_t rngSeed, uint32_t w, uint32_t h, float fov, floa
     st3(out + 3 * i, pixelToRayDir(pv, pu, (float)w, (float)h, tanTheta));
   }
 }
+int orc_nif_eval_partials(const b200rt_nif_desc* nif, const float* uv, size_t n, float* out, int threads, int halfChunk) {
+  const NifHost host(*nif);
+#pragma omp parallel for schedule(static) num_threads(threadsOr(threads))
+  for (long long i = 0; i < (long long)n; ++i) nifForward(host, uv[2 * i], uv[2 * i + 1], out + 3 * i, halfChunk);
+  return 0;
+}
+
 int orc_nif_eval(const b200rt_nif_desc* nif, const float* uv, size_t n, float* out, int threads) {
   const NifHost host(*nif);
 #pragma omp parallel for schedule(static) num_threads(threadsOr(threads))

@@ -162,6 +162,16 @@ class Oracle:
             raise RuntimeError(f"{self.kind} oracle has no NIF")
         return out
 
+    def nif_eval_partials(self, nif, uv, half_chunk=16, threads=0):
+        """NIF forward with fp16 partials modelled (the IPU's partialsType=half, src/IpuScene.cpp:256-262). Port only."""
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], 3), np.float32)
+        d, keep = nif.to_desc()
+        f = self._f("nif_eval_partials")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+        assert f(C.byref(d), capi.ptr(uv), uv.shape[0], capi.ptr(out), threads, half_chunk) == 0
+        return out
+
     def dir_to_uv(self, dirs, rotation_radians=0.0):
         dirs = np.ascontiguousarray(dirs, np.float32)
         out = np.zeros((dirs.shape[0], 2), np.float32)
