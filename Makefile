@@ -30,7 +30,7 @@ $(PKG)/libb200rt.so: $(CSRC)/b200rt.o $(CSRC)/nif.o
 	$(NVCC) $(ARCH) -shared -ccbin $(CXX) -o $@ $^ -cudart static
 
 HOST_SRCS := $(HOST)/scene_build.cpp $(HOST)/gltf_import.cpp $(HOST)/image_io.cpp $(HOST)/scene_capi.cpp \
-             $(HOST)/scene_import.cpp
+             $(HOST)/scene_import.cpp $(HOST)/keras_hdf5.cpp
 $(PKG)/libb200rt_scene.so: $(HOST_SRCS) $(HOST)/scene_build.hpp $(HOST)/rt_types.hpp $(HOST)/mini_json.hpp \
                            $(CSRC)/rt_math.h include/b200rt_scene.h include/b200rt.h
 	$(CXX) $(HOSTFLAGS) -shared -o $@ $(HOST_SRCS)

@@ -63,6 +63,25 @@ typedef struct b200rt_nif_metadata {
 } b200rt_nif_metadata;
 int  b200rt_read_nif_metadata(const char* path, b200rt_nif_metadata* out);
 
+/* NIF weights: the Keras "h5" model the reference loads (`<assets.extra>/converted.hdf5`, src/IpuScene.cpp:177) through
+ * Hdf5Model (src/keras/Hdf5Model.cpp:8-133): root attributes keras_version / backend / model_config (a "Functional"
+ * model; Dense layers kept in order, InputLayer / Concatenate ignored, anything else an error) and
+ * /model_weights/<name>/<name>/{kernel:0, bias:0}. Read by a self-contained reader of the classic HDF5 layout
+ * (host/keras_hdf5.cpp; libhdf5 is not a dependency); float32 datasets are rounded to fp16. The returned layers point
+ * into the model handle and stay valid until b200rt_keras_hdf5_close. */
+typedef struct b200rt_keras_model b200rt_keras_model;
+typedef struct b200rt_keras_layer {
+  char name[64];
+  char activation[32];
+  b200rt_nif_layer layer;   /* in/out features, fp16 kernel [in][out], fp16 bias or NULL, relu = (activation == "relu") */
+} b200rt_keras_layer;
+int         b200rt_keras_hdf5_open(const char* path, b200rt_keras_model** out);
+void        b200rt_keras_hdf5_close(b200rt_keras_model* model);
+uint32_t    b200rt_keras_hdf5_num_layers(const b200rt_keras_model* model);
+int         b200rt_keras_hdf5_layer(const b200rt_keras_model* model, uint32_t index, b200rt_keras_layer* out);
+const char* b200rt_keras_hdf5_version(const b200rt_keras_model* model);
+const char* b200rt_keras_last_error(void);
+
 /* The reference's serialised scene: `SceneRef` written by Serialiser<16> (include/serialisation/Serialiser.hpp:24-64,
  * serialisation.hpp:34-52) -- the byte stream IpuScene uploads (src/IpuScene.cpp:52, :665) and the device reads back
  * in place (deserialisation.hpp:29-59). b200rt_scene_desc_from_blob fills `out` with pointers INTO `blob` (zero copy:

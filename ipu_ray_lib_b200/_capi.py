@@ -118,6 +118,10 @@ class NifMetadata(C.Structure):
     ]
 
 
+class KerasLayer(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("activation", C.c_char * 32), ("layer", NifLayer)]
+
+
 RAY_CALLBACK = C.CFUNCTYPE(None, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
 
 # Every symbol include/b200rt.h declares; tests check the built library exports each one.
@@ -135,6 +139,8 @@ B200RT_SCENE_SYMBOLS = [
     "b200rt_init_ray_stream", "b200rt_scale_rgb", "b200rt_visualise_hits",
     "b200rt_write_exr", "b200rt_write_pfm", "b200rt_read_nif_metadata", "b200rt_sincos",
     "b200rt_scene_desc_from_blob", "b200rt_scene_blob_write",
+    "b200rt_keras_hdf5_open", "b200rt_keras_hdf5_close", "b200rt_keras_hdf5_num_layers", "b200rt_keras_hdf5_layer",
+    "b200rt_keras_hdf5_version", "b200rt_keras_last_error",
 ]
 
 _lib = None
@@ -212,6 +218,15 @@ def scene_lib() -> C.CDLL:
         L.b200rt_scene_blob_write.argtypes = [C.POINTER(SceneDesc), C.c_void_p, C.c_size_t]
         L.b200rt_scene_blob_write.restype = C.c_size_t
         L.b200rt_sincos.restype = None
+        L.b200rt_keras_hdf5_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.b200rt_keras_hdf5_close.argtypes = [C.c_void_p]
+        L.b200rt_keras_hdf5_close.restype = None
+        L.b200rt_keras_hdf5_num_layers.argtypes = [C.c_void_p]
+        L.b200rt_keras_hdf5_num_layers.restype = C.c_uint32
+        L.b200rt_keras_hdf5_layer.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(KerasLayer)]
+        L.b200rt_keras_hdf5_version.argtypes = [C.c_void_p]
+        L.b200rt_keras_hdf5_version.restype = C.c_char_p
+        L.b200rt_keras_last_error.restype = C.c_char_p
         _scene_lib = L
     return _scene_lib
 

@@ -54,23 +54,23 @@ struct NifWeightsFile {
   struct Layer { std::uint32_t in, out, relu; std::vector<std::uint16_t> kernel, bias; };
   std::vector<Layer> layers;
 
+  // The reference's own container: the Keras h5 model `converted.hdf5` (src/IpuScene.cpp:177, src/keras/Hdf5Model.cpp),
+  // read by the self-contained reader in host/keras_hdf5.cpp.
   static NifWeightsFile load(const std::string& path) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) throw std::runtime_error("Could not open NIF weights '" + path + "'");
-    auto rd = [&](void* p, size_t n) { if (!f.read((char*)p, (std::streamsize)n)) throw std::runtime_error("truncated NIF weights file"); };
-    char magic[4];
-    std::uint32_t version, n;
+    b200rt_keras_model* m = nullptr;
+    if (b200rt_keras_hdf5_open(path.c_str(), &m) != 0) throw std::runtime_error(b200rt_keras_last_error());
+    struct Close { b200rt_keras_model* m; ~Close() { b200rt_keras_hdf5_close(m); } } close{m};
     NifWeightsFile w;
-    rd(magic, 4); rd(&version, 4); rd(&w.embedding, 4); rd(&n, 4); rd(&w.max, 4); rd(w.mean, 12); rd(&w.logToneMap, 4);
-    if (std::memcmp(magic, "B2NF", 4) != 0 || version != 1 || n > 16) throw std::runtime_error("bad NIF weights header");
+    const std::uint32_t n = b200rt_keras_hdf5_num_layers(m);
+    if (n == 0 || n > 16) throw std::runtime_error("implausible number of Dense layers in '" + path + "'");
     w.layers.resize(n);
-    for (auto& L : w.layers) {
-      std::uint32_t hasBias;
-      rd(&L.in, 4); rd(&L.out, 4); rd(&L.relu, 4); rd(&hasBias, 4);
-      if ((std::uint64_t)L.in * L.out > (1u << 24)) throw std::runtime_error("implausible NIF layer shape");
-      L.kernel.resize((size_t)L.in * L.out);
-      rd(L.kernel.data(), L.kernel.size() * 2);
-      if (hasBias) { L.bias.resize(L.out); rd(L.bias.data(), L.bias.size() * 2); }
+    for (std::uint32_t i = 0; i < n; ++i) {
+      b200rt_keras_layer kl;
+      if (b200rt_keras_hdf5_layer(m, i, &kl) != 0) throw std::runtime_error(b200rt_keras_last_error());
+      Layer& L = w.layers[i];
+      L.in = kl.layer.in_features; L.out = kl.layer.out_features; L.relu = (std::uint32_t)kl.layer.relu;
+      L.kernel.assign(kl.layer.kernel_f16, kl.layer.kernel_f16 + (size_t)L.in * L.out);
+      if (kl.layer.bias_f16) L.bias.assign(kl.layer.bias_f16, kl.layer.bias_f16 + L.out);
     }
     return w;
   }
@@ -94,7 +94,7 @@ class B200Scene {
       b200rt_nif_metadata md{};
       if (b200rt_read_nif_metadata((assetPath + "/nif_metadata.txt").c_str(), &md) != 0)
         throw std::runtime_error(b200rt_scene_last_error());
-      nif_ = NifWeightsFile::load(assetPath + "/converted.b200nif");
+      nif_ = NifWeightsFile::load(assetPath + "/converted.hdf5");
       nif_.max = md.max;
       std::copy(md.mean, md.mean + 3, nif_.mean);
       nif_.logToneMap = (std::uint32_t)md.log_tone_map;

@@ -1,13 +1,13 @@
 """NIF environment-light weights: container, synthetic generator and file format.
 
-The reference loads a Keras HDF5 file (src/keras/Hdf5Model.cpp) that is missing from its checkout
-(.MISSING_LARGE_BLOBS) and whose reader needs libhdf5 (absent here). This module keeps the layer
-list data-driven exactly like the reference (a list of Dense layers: fp16 kernel [in,out],
-optional fp16 bias, relu/linear) and provides
+The reference loads a Keras h5 file (src/keras/Hdf5Model.cpp) that is missing from its checkout
+(.MISSING_LARGE_BLOBS). This module keeps the layer list data-driven exactly like the reference (a list
+of Dense layers: fp16 kernel [in,out], optional fp16 bias, relu/linear) and provides
   * ``NifWeights.synthetic`` — fixed-seed random weights in the architecture the shipped metadata
     implies (embedding 12, hidden 320, 6 hidden layers with the encoded input concatenated into the
     4th, 3 linear outputs), and
-  * a trivial ``.npz`` container so trained weights exported from Keras can be dropped in.
+  * ``NifWeights.load`` / ``save`` — the reference's own container, a Keras h5 model file, read by the C++ reader of
+    ``host/keras_hdf5.cpp`` (shared with ``B200Scene::loadNifModel``) and written by ``keras_h5.py``.
 """
 from __future__ import annotations
 
@@ -66,25 +66,45 @@ class NifWeights:
         w.log_tone_map = bool(md.log_tone_map)
         return w
 
-    def save(self, path) -> None:
-        arrays = {"embedding_dimension": np.int32(self.embedding_dimension), "max": np.float32(self.max),
-                  "mean": np.asarray(self.mean, np.float32), "log_tone_map": np.int32(self.log_tone_map),
-                  "num_layers": np.int32(len(self.layers))}
-        for i, l in enumerate(self.layers):
-            arrays[f"kernel_{i}"] = l.kernel
-            arrays[f"relu_{i}"] = np.int32(l.relu)
-            if l.bias is not None:
-                arrays[f"bias_{i}"] = l.bias
-        np.savez(path, **arrays)
+    def save(self, path, *, float32: bool = False) -> None:
+        """Write the layer list as a Keras h5 model (the container the reference loads, src/keras/Hdf5Model.cpp)."""
+        from .keras_h5 import write_keras_h5
+
+        write_keras_h5(path, self, float32=float32)
 
     @classmethod
-    def load(cls, path) -> "NifWeights":
-        z = np.load(path)
-        w = cls(embedding_dimension=int(z["embedding_dimension"]), max=float(z["max"]),
-                mean=tuple(float(x) for x in z["mean"]), log_tone_map=bool(z["log_tone_map"]))
-        for i in range(int(z["num_layers"])):
-            bias = z[f"bias_{i}"].astype(np.float16) if f"bias_{i}" in z else None
-            w.layers.append(DenseLayer(z[f"kernel_{i}"].astype(np.float16), bias, bool(z[f"relu_{i}"])))
+    def load(cls, path, metadata_path=None) -> "NifWeights":
+        """Load a Keras h5 model through the C++ reader (host/keras_hdf5.cpp). Decode parameters come from
+        ``nif_metadata.txt`` (default: next to the file), as in IpuScene::loadNifModel (src/IpuScene.cpp:174-187)."""
+        lib = capi.scene_lib()
+        h = C.c_void_p()
+        if lib.b200rt_keras_hdf5_open(str(path).encode(), C.byref(h)) != 0:
+            raise RuntimeError(lib.b200rt_keras_last_error().decode())
+        try:
+            layers = []
+            for i in range(lib.b200rt_keras_hdf5_num_layers(h)):
+                kl = capi.KerasLayer()
+                if lib.b200rt_keras_hdf5_layer(h, i, C.byref(kl)) != 0:
+                    raise RuntimeError(lib.b200rt_keras_last_error().decode())
+                L = kl.layer
+                k = np.ctypeslib.as_array(C.cast(L.kernel_f16, C.POINTER(C.c_uint16)), (L.in_features, L.out_features))
+                kern = k.view(np.float16).copy()
+                bias = None
+                if L.bias_f16:
+                    bias = np.ctypeslib.as_array(C.cast(L.bias_f16, C.POINTER(C.c_uint16)), (L.out_features,)).view(np.float16).copy()
+                layers.append(DenseLayer(kern, bias, bool(L.relu)))
+        finally:
+            lib.b200rt_keras_hdf5_close(h)
+        md_path = Path(metadata_path) if metadata_path else Path(path).with_name("nif_metadata.txt")
+        if md_path.exists():
+            md = capi.NifMetadata()
+            if lib.b200rt_read_nif_metadata(str(md_path).encode(), C.byref(md)) != 0:
+                raise RuntimeError(lib.b200rt_scene_last_error().decode())
+            w = cls(embedding_dimension=md.embedding_dimension, max=float(md.max), mean=tuple(float(x) for x in md.mean),
+                    log_tone_map=bool(md.log_tone_map))
+        else:
+            w = cls(embedding_dimension=layers[0].kernel.shape[0] // 4)
+        w.layers = layers
         return w
 
     def flops_per_sample(self) -> int:

@@ -55,3 +55,31 @@ def test_cli_shadow_trace_normals_and_imported_scene(tmp_path, port):
     want = scene.init_ray_stream(160, 120, s.fov)
     port.path_trace(s, want)
     assert_streams_identical(rays, want, "trace --mesh-file test_scene.dae --load-normals")
+
+
+def test_cli_loads_a_keras_h5_nif_like_the_reference(tmp_path, port):
+    """trace --nif-hdri <assets.extra>: nif_metadata.txt + converted.hdf5 (src/IpuScene.cpp:174-187), the weights read
+    by the HDF5 reader; the NIF-lit image agrees with the oracle within the NIF tolerance and the hit records exactly."""
+    import shutil
+
+    from ipu_ray_lib_b200.nif import NifWeights
+
+    extra = tmp_path / "assets.extra"
+    extra.mkdir()
+    md = ROOT / "assets/nif/urban_alley_01_4k_fp16_yuv/assets.extra/nif_metadata.txt"
+    shutil.copy(md, extra / "nif_metadata.txt")
+    nif = NifWeights.from_metadata(md, seed=99)
+    nif.save(extra / "converted.hdf5")
+    w, h, spp = 200, 120, 4
+    rays, log = run_trace(tmp_path, "--scene", "spheres", "-w", str(w), "-h", str(h), "--samples", str(spp), "--ipus", "1",
+                          "--nif-hdri", str(extra), "--hdri-rotation", "35", "--max-nif-batch-size", "4096")
+    assert "Loaded NIF model" in log
+    s = scene.HostScene.builtin("spheres").configure(w, h, path_trace=True, samples=spp, seed=1442)
+    want = scene.init_ray_stream(w, h, s.fov)
+    port.path_trace(s, want, nif=NifWeights.load(extra / "converted.hdf5"), hdri_rotation=35.0)
+    a, b = rays.copy(), want.copy()
+    a["rgb"] = 0
+    b["rgb"] = 0
+    assert a.tobytes() == b.tobytes()
+    err = np.abs(rays["rgb"].astype(np.float64) - want["rgb"]).sum() / np.abs(want["rgb"]).sum()
+    assert err < 8e-4, err

@@ -3,8 +3,11 @@
 Tolerance statement: features, weights and layer outputs are fp16 on both sides; the oracle accumulates each
 dot product in fp32 in k order, the GPU in tile order (tensor cores) — pre-rounding sums differ by ~1e-6
 relative, which flips an fp16 rounding of a layer output now and then (1 fp16 ulp = 1e-3 relative of ONE of 320
-activations). After 7 layers and exp(3.43 x) the bgr outputs agree to a few 1e-3 relative: we require
-max relative error < 3e-2 and mean relative error < 2e-3 over 100k random lookups.
+activations). Measured on a B200 over 100 k random lookups of the headline model (scripts/nif_tolerance.py,
+profiles/r02_nif_tolerance.txt): max relative error 3.4e-3, mean 1.6e-4, 99.9th percentile 1.9e-3. The tests require
+max < 1.5e-2 and mean < 8e-4 (about 5x the measurement).
+The part nothing can pin (the reference has no CPU NIF, and the IPU accumulated in fp16 partials,
+src/IpuScene.cpp:256-262) is bounded with a model of that option: test_fp16_partials_model_bounds_the_unpinned_gap.
 """
 import numpy as np
 import pytest
@@ -12,7 +15,7 @@ import pytest
 from ipu_ray_lib_b200 import _capi as capi, scene
 from ipu_ray_lib_b200.nif import NifWeights
 
-MAX_REL, MEAN_REL = 3e-2, 2e-3
+MAX_REL, MEAN_REL = 1.5e-2, 8e-4
 
 
 def numpy_nif(w: NifWeights, uv):
@@ -53,6 +56,19 @@ def test_oracle_nif_against_numpy(port):
     rel = np.abs(got - want) / np.abs(want)
     assert rel.max() < MAX_REL and rel.mean() < MEAN_REL
     assert np.all(np.isfinite(got)) and got.min() > 0
+
+
+def test_fp16_partials_model_bounds_the_unpinned_gap(port):
+    """The reference ran the MLP with partialsType = half on the IPU (src/IpuScene.cpp:256-262); this build accumulates
+    in fp32 (TMEM). The oracle can model fp16 partials (running sum rounded to fp16 every 16 products): the two
+    contracts differ by ~2e-3 mean / ~1.4e-2 max relative in the decoded radiance -- that is the size of what stays
+    unpinned, an order of magnitude above the GPU-vs-oracle error and far below Monte-Carlo noise at 1000 spp."""
+    w = NifWeights.synthetic(seed=1442)
+    uv = np.random.default_rng(2).uniform(0, 1, (20000, 2)).astype(np.float32)
+    a, b = port.nif_eval(w, uv), port.nif_eval_partials(w, uv, half_chunk=16)
+    rel = np.abs(a - b) / np.abs(a)
+    assert 5e-4 < rel.mean() < 4e-3 and rel.max() < 3e-2
+    assert np.array_equal(port.nif_eval_partials(w, uv, half_chunk=0), a)
 
 
 def test_oracle_nif_is_data_driven(port):
@@ -103,8 +119,11 @@ def test_gpu_nif_other_architectures(port, box_scene):
     nobias.layers = [DenseLayer((rng.standard_normal((48, 128)) * 0.2).astype(np.float16), None, True),
                      DenseLayer((rng.standard_normal((128, 128)) * 0.12).astype(np.float16), None, True),
                      DenseLayer((rng.standard_normal((128, 3)) * 0.1).astype(np.float16), None, False)]
+    odd = NifWeights.synthetic(seed=6, hidden=200, hidden_layers=4, concat_at=2)   # zero-padded to 320 columns
+    narrow = NifWeights.synthetic(seed=7, hidden=100, hidden_layers=2, concat_at=1)  # zero-padded to 160 columns
+    ragged = NifWeights.synthetic(seed=8, hidden=77, hidden_layers=3, concat_at=1)   # not a multiple of 16
     with B200Scene(box_scene.configure(64, 64)) as g:
-        for w in (small, nobias):
+        for w in (small, nobias, odd, narrow, ragged):
             g.load_nif_model(w)
             got, want = g.nif_eval(uv), port.nif_eval(w, uv)
             assert np.allclose(got, want, rtol=MAX_REL, atol=2e-3)
@@ -127,6 +146,10 @@ def test_nif_lit_path_trace_matches_oracle(port, name, chunk):
         got = base.copy()
         g.execute(got, samples_per_chunk=chunk)
         st = g.stats()
+        g.set_max_nif_batch_size(1000)  # IpuScene::setMaxNifBatchSize: serial NIF launches of <= 1000 rays, same image
+        again = base.copy()
+        g.execute(again, samples_per_chunk=chunk)
+        assert again.tobytes() == got.tobytes() and g.stats()["nif_kernel_launches"] > st["nif_kernel_launches"]
     assert st["escaped_samples"] == cw["escaped_samples"] and st["samples"] == cw["samples"]
     a = got.copy(); b = want.copy()
     a["rgb"] = 0; b["rgb"] = 0
@@ -136,20 +159,3 @@ def test_nif_lit_path_trace_matches_oracle(port, name, chunk):
     # per-pixel: allow the rare fp16 argument flip caused by libm-vs-CUDA acos/atan2 ulp differences
     rel = np.abs(got["rgb"] - want["rgb"]).max(axis=1) / np.maximum(np.abs(want["rgb"]).max(axis=1), 1e-6)
     assert np.mean(rel > MAX_REL) < 5e-3
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_cta_pair_kernels_match_oracle_too(mode):
-    """The opt-in cta_group::2 kernels (B200RT_NIF_PAIR=1: pair version of the product kernel, 2: pair + fully overlapped
-    pipeline; read once per process, hence the subprocess) pass the same NIF parity tests, including tile counts that
-    leave the peer CTA of the last pair without a tile."""
-    import os
-    import subprocess
-    import sys
-
-    env = dict(os.environ, B200RT_NIF_PAIR=mode)
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
-                        "gpu_nif_eval_matches_oracle or nif_lit_path_trace"], env=env, capture_output=True, text=True,
-                       timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
