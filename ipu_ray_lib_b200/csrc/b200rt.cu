@@ -84,7 +84,7 @@ struct b200rt_scene {
   b200rt_scene_desc desc{};  // scalars only are used after creation
   rt::DevScene dev{};
   uint32_t nodeBytes = 0, pairBytes = 0;
-  DeviceBuffer nodes, pairs, leafOrig, geoms, triVerts, triNormals, spheres, discs, matIDs, materials;
+  DeviceBuffer nodes, pairs, leafOrig, leafInfo, geoms, triVerts, triNormals, spheres, discs, matIDs, materials;
   DeviceBuffer workCounter, counters, primA, primB;
   DeviceBuffer rays;                                   // device copy of the stream (host-buffer entry point)
   DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
@@ -98,7 +98,7 @@ struct b200rt_scene {
   ~b200rt_scene() {
     cudaSetDevice(device);
     if (nif) rt::nif_destroy(nif);
-    for (DeviceBuffer* b : {&nodes, &pairs, &leafOrig, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
+    for (DeviceBuffer* b : {&nodes, &pairs, &leafOrig, &leafInfo, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
                             &workCounter, &counters, &primA, &primB, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
                             &escapeCount, &wfRayO, &wfRayD, &wfNrm, &wfThr, &wfRng, &wfHitA, &wfHitB, &wfQ0, &wfQ1,
                             &wfCounts})
@@ -232,7 +232,7 @@ cudaError_t run_path(b200rt_scene& sc, const LaunchPlan& L, bool nif, const rt::
 // Per-kernel device timing with CUDA event pairs recorded on the launching stream.
 struct KernelTimer {
   enum Kind { TRACE = 0, NIF = 1, ACCUM = 2, SHADE = 3 };
-  struct Span { cudaEvent_t a, b; Kind kind; };
+  struct Span { cudaEvent_t a, b; Kind kind; int launches; };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
@@ -240,14 +240,14 @@ struct KernelTimer {
     if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
     return pool[used++];
   }
-  void begin(Kind k, cudaStream_t st) { Span s{get(), get(), k}; cudaEventRecord(s.a, st); spans.push_back(s); }
-  void end(cudaStream_t st) { cudaEventRecord(spans.back().b, st); }
+  void begin(Kind k, cudaStream_t st) { Span s{get(), get(), k, 1}; cudaEventRecord(s.a, st); spans.push_back(s); }
+  void end(cudaStream_t st, int launches = 1) { spans.back().launches = launches; cudaEventRecord(spans.back().b, st); }
   void collect(b200rt_trace_stats& out) {
     for (const Span& s : spans) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, s.a, s.b) != cudaSuccess) continue;
       if (s.kind == TRACE) { out.trace_kernel_ms += ms; out.trace_kernel_launches += 1; }
-      else if (s.kind == NIF) { out.nif_kernel_ms += ms; out.nif_kernel_launches += 1; }
+      else if (s.kind == NIF) { out.nif_kernel_ms += ms; out.nif_kernel_launches += (uint64_t)s.launches; }
       else if (s.kind == SHADE) { out.shade_kernel_ms += ms; out.shade_kernel_launches += 1; }
       else out.accumulate_kernel_ms += ms;
     }
@@ -393,7 +393,7 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
         CU_TRY(sc.wfCounts.reserve(16));
         w.b.rayO = (float4*)sc.wfRayO.p; w.b.rayD = (float4*)sc.wfRayD.p; w.b.nrm = (float4*)sc.wfNrm.p;
         w.b.thr = (float4*)sc.wfThr.p; w.b.rng = (uint4*)sc.wfRng.p;
-        w.b.hitA = (float4*)sc.wfHitA.p; w.b.hitB = needBary ? (float4*)sc.wfHitB.p : nullptr;
+        w.b.hitA = (float2*)sc.wfHitA.p; w.b.hitB = needBary ? (float4*)sc.wfHitB.p : nullptr;
         w.b.queue[0] = (uint32_t*)sc.wfQ0.p; w.b.queue[1] = (uint32_t*)sc.wfQ1.p;
         w.b.counts = (uint32_t*)sc.wfCounts.p;
         w.lastSample = first + count - 1;
@@ -502,7 +502,7 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
                                             (const uint32_t*)sc.escapeCount.p, (uint32_t)std::min<size_t>((size_t)c * n, 0xFFFFFFFFull),
                                             (uint32_t)std::min<size_t>(sc.maxNifBatch, 0xFFFFFFFFull), (float*)sc.slotEnv.p, sc.stream,
                                             &nifLaunches);
-          timer.end(sc.stream);
+          timer.end(sc.stream, nifLaunches);
           if (rc != 0) return fail(B200RT_ERR_CUDA, std::string("NIF evaluation failed: ") + rt::nif_last_error());
           launches += (uint64_t)nifLaunches;
         }
@@ -634,6 +634,7 @@ int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
   sc->pairBytes = tables.pairs.numPairs * 48u;
   CU_TRY(sc->pairs.upload(tables.pairs.words.data(), sc->pairBytes));
   CU_TRY(sc->leafOrig.upload(tables.pairs.leafOrig.data(), tables.pairs.leafOrig.size() * 4));
+  CU_TRY(sc->leafInfo.upload(tables.pairs.leafInfo.data(), tables.pairs.leafInfo.size() * 4));
   CU_TRY(sc->geoms.upload(tables.geoms.data(), tables.geoms.size() * sizeof(rt::GeomEntry)));
   CU_TRY(sc->triVerts.upload(tables.triVerts.data(), tables.triVerts.size() * sizeof(float)));
   if (d->num_normals) CU_TRY(sc->triNormals.upload(tables.triNormals.data(), tables.triNormals.size() * sizeof(float)));
@@ -660,6 +661,10 @@ int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
   sc->dev.rootRef = tables.pairs.rootRef;
   sc->dev.rootGeom = tables.pairs.rootGeom;
   sc->dev.boundsFinite = tables.pairs.boundsFinite ? 1u : 0u;
+  sc->dev.leafInfo = (const uint4*)sc->leafInfo.p;
+  sc->dev.numTris = d->num_tris;
+  sc->dev.numSpheres = d->num_spheres;
+  sc->dev.trisBounded = tables.trisBounded ? 1u : 0u;
   {
     struct Node { float mn[3]; uint32_t x; uint16_t d[3]; uint16_t g; };
     const Node& r = *static_cast<const Node*>(d->bvh_nodes);

@@ -15,6 +15,7 @@ namespace rt {
 struct PairTable {
   std::vector<uint32_t> words;     // 12 per pair
   std::vector<uint32_t> leafOrig;  // 2 per pair
+  std::vector<uint32_t> leafInfo;  // 4 per primitive slot (triangles, spheres, discs): DevScene::leafInfo
   uint32_t numPairs = 0;
   uint32_t rootRef = 0, rootGeom = kInvalidGeom;
   uint32_t maxDepth = 0;           // deepest leaf (root = depth 0) = bound on the traversal stack
@@ -23,13 +24,35 @@ struct PairTable {
 
 // `primCount[g]` = number of primitives geometry g may be addressed with (mesh: its triangles; sphere/disc: unbounded,
 // pass 0xFFFFFFFF). Returns an empty string on success, else what is wrong with the node array.
+// numTris / numSpheres / numDiscs size the per-primitive table (leafInfo).
 inline std::string build_pair_table(const void* nodes24, uint32_t numNodes, const GeomEntry* geoms, uint32_t numGeoms,
-                                    const uint32_t* primCount, PairTable& out) {
+                                    const uint32_t* primCount, uint32_t numTris, uint32_t numSpheres, uint32_t numDiscs,
+                                    PairTable& out) {
   struct Node { float mn[3]; uint32_t primOrSecond; uint16_t d[3]; uint16_t geomID; };
   static_assert(sizeof(Node) == 24, "CompactBVH2Node");
   const Node* nodes = static_cast<const Node*>(nodes24);
   out = PairTable{};
   if (numNodes == 0) return "empty node array";
+  const uint64_t numSlots = (uint64_t)numTris + numSpheres + numDiscs;
+  if (numSlots > kLeafIndexMask) return "more than 2^30 primitives";
+  out.leafInfo.assign((size_t)numSlots * 4, 0u);
+  for (size_t i = 0; i < (size_t)numSlots; ++i) {
+    out.leafInfo[4 * i] = kInvalidGeom; out.leafInfo[4 * i + 1] = kInvalidPrim; out.leafInfo[4 * i + 2] = 0xFFFFFFFFu;
+  }
+  // a leaf: record geomID / reported primID / node index under its primitive (the lowest node index wins when a
+  // primitive sits in several leaves: that is the leaf the reference's pre-order walk meets first)
+  auto note_leaf = [&](uint32_t node, uint32_t ref, std::string& err) {
+    const uint32_t type = ref >> 30, index = ref & kLeafIndexMask;
+    const uint64_t limit = type == 0u ? numTris : (type == 1u ? numSpheres : numDiscs);
+    if (index >= limit) { err = "leaf primitive index out of range"; return; }
+    const size_t slot = (size_t)index + (type == 0u ? 0u : (type == 1u ? numTris : numTris + numSpheres));
+    uint32_t* info = &out.leafInfo[4 * slot];
+    if (node < info[2]) {
+      info[0] = nodes[node].geomID;
+      info[1] = type == 0u ? nodes[node].primOrSecond : 0u;
+      info[2] = node;
+    }
+  };
 
   auto child_ref = [&](uint32_t i, uint32_t& ref, std::string& err) {
     const Node& n = nodes[i];
@@ -91,8 +114,9 @@ inline std::string build_pair_table(const void* nodes24, uint32_t numNodes, cons
     uint32_t* w = &out.words[(size_t)p * 12];
     for (int side = 0; side < 2; ++side) {
       const Node& c = nodes[kids[side]];
-      uint32_t ref = pairOf[kids[side]];
+      uint32_t ref = kRefInner | pairOf[kids[side]];
       child_ref(kids[side], ref, err);
+      if (err.empty() && c.geomID != kInvalidGeom) note_leaf(kids[side], ref, err);
       if (!err.empty()) return err;
       uint32_t* d = w + 6 * side;
       std::memcpy(d, c.mn, 12);
@@ -103,9 +127,10 @@ inline std::string build_pair_table(const void* nodes24, uint32_t numNodes, cons
     }
   }
   out.rootGeom = nodes[0].geomID;
-  out.rootRef = 0u;
+  out.rootRef = kRefInner | 0u;
   if (out.rootGeom != kInvalidGeom) {
     child_ref(0u, out.rootRef, err);
+    if (err.empty()) note_leaf(0u, out.rootRef, err);
     if (!err.empty()) return err;
   }
   return std::string();

@@ -41,7 +41,8 @@ struct alignas(8) GeomEntry {
 struct DevScene {
   const uint2* nodes;        // CompactBVH2Node[], 24 B each, UNCHANGED from the caller (read as 3 x 8 B)
   const GeomEntry* geoms;    // [num_geometry]
-  const float4* triVerts;    // [num_tris][3]  p0,p1,p2 gathered from Triangle[] + Vec3fa[] (w unused)
+  const float4* triVerts;    // [3][num_tris][3]  p0,p1,p2 gathered from Triangle[] + Vec3fa[] (w unused); copy 0 as
+                             // given, copies 1 and 2 with the components rotated for kz = 0 / kz = 1 (see tri_test_fast)
   const float4* triNormals;  // [num_tris][3]  vertex normals, or nullptr when the scene has none
   const float4* spheres;     // {x,y,z,radius}
   const float* discs;        // {nx,ny,nz,r,cx,cy,cz}
@@ -56,6 +57,10 @@ struct DevScene {
   uint32_t rootRef;          // root as a child reference: pair index 0, or the leaf reference when the tree is one leaf
   uint32_t rootGeom;         // geomID of the root (kInvalidGeom when it is an inner node)
   uint32_t boundsFinite;     // 1 = every node bound is finite: the NaN-free fast slab test is allowed
+  // per-primitive table of the streaming kernels, indexed by prim_slot(leaf reference)
+  const uint4* leafInfo;     // {geomID, primID as the reference reports it, reference node index of its (first) leaf, -}
+  uint32_t numTris, numSpheres;
+  uint32_t trisBounded;      // 1 = every triangle vertex is finite and |coordinate| < 2^20: tri_test_fast is allowed
 };
 
 RT_HD float bits_f(uint32_t u) {
@@ -249,9 +254,10 @@ RT_HD float disc_test(const float* __restrict__ p, V3 o, V3 d) {
 //   word  4     L.dx | L.dy << 16 (f16)  word 10      R.dx | R.dy << 16
 //   word  5     L.dz | L.geomID << 16    word 11      R.dz | R.geomID << 16
 //
-// where ref = pair index of the child if it is an inner node (geomID == 0xFFFF), else the leaf
+// where ref = kRefInner | pair index of the child if it is an inner node (geomID == 0xFFFF), else the leaf
 // reference  type << 30 | index  (type 0: global triangle index; 1: sphere index; 2: disc index) — the
 // GeomRef/MeshInfo lookup of primLookup (codelets/TraceCodelets.cpp:127-140) folded in at build time.
+// One unsigned comparison therefore tells a leaf (ref < kRefInner) from an inner node.
 // Bounds are the node's own bits (fp32 min, fp16 extents): the box arithmetic is the reference's.
 // A traversal step loads one aligned 48-byte record (3 x LDS.128 / LDG.128) instead of two 24-byte
 // nodes from unrelated addresses (6 x 8 B), and a leaf test needs no geometry-table lookup.
@@ -262,6 +268,12 @@ struct PairWords {
   uint4 q0, q1, q2;
 };
 constexpr uint32_t kLeafIndexMask = 0x3FFFFFFFu;
+constexpr uint32_t kRefInner = 0xC0000000u;  // child reference of an inner node: kRefInner | pair index
+constexpr uint32_t kRefNone = 0xFFFFFFFFu;   // "no node": end of a query / no hit yet (never a valid reference)
+constexpr uint32_t kRefDone = 0xFFFFFFFEu;   // streaming kernels: the lane has run out of rays
+RT_HD bool ref_is_leaf(uint32_t ref) { return ref < kRefInner; }
+RT_HD bool ref_is_inner(uint32_t ref) { return ref - kRefInner < 0x3FFFFFFEu; }
+RT_HD uint32_t ref_pair(uint32_t ref) { return ref & kLeafIndexMask; }
 
 template <bool kShared>
 RT_HD PairWords fetch_pair(const uint4* __restrict__ pairs, uint32_t idx) {
@@ -405,7 +417,7 @@ RT_HD void pair_closest_hit(const DevScene& sc, const uint4* __restrict__ pairs,
   };
   while (!done) {
     while (!done && geom == kInvalidGeom) {
-      const PairWords w = fetch_pair<kShared>(pairs, ref);
+      const PairWords w = fetch_pair<kShared>(pairs, ref_pair(ref));
       if (kCount) nodeVisits += 2;
       bool h0, h1;
       float e0, e1;
@@ -413,7 +425,7 @@ RT_HD void pair_closest_hit(const DevScene& sc, const uint4* __restrict__ pairs,
       else pair_slabs<false>(w, o, inv, tMin, hit.t, h0, h1, e0, e1);
       if (h0 | h1) {
         const bool goL = h0 && (!h1 || !(e1 < e0));  // ties go to the first child, like pre-order
-        const uint32_t k0 = ref * 2u;
+        const uint32_t k0 = ref_pair(ref) * 2u;
         if (h0 && h1) stack[sp++] = make_uint2(goL ? k0 + 1u : k0, f_bits(goL ? e1 : e0));
         key = goL ? k0 : k0 + 1u;
         ref = goL ? w.q0.w : w.q2.y;
@@ -448,14 +460,14 @@ RT_HD bool pair_any_hit(const DevScene& sc, const uint4* __restrict__ pairs, V3 
   while (true) {
     bool needPop = false;
     if (geom == kInvalidGeom) {
-      const PairWords w = fetch_pair<kShared>(pairs, ref);
+      const PairWords w = fetch_pair<kShared>(pairs, ref_pair(ref));
       if (kCount) nodeVisits += 2;
       bool h0, h1;
       float e0, e1;
       if (fast) pair_slabs<true>(w, o, inv, tMin, tMax, h0, h1, e0, e1);
       else pair_slabs<false>(w, o, inv, tMin, tMax, h0, h1, e0, e1);
       if (h0 | h1) {
-        if (h0 && h1) stack[sp++] = ref * 2u + 1u;
+        if (h0 && h1) stack[sp++] = ref_pair(ref) * 2u + 1u;
         const bool goL = h0;
         ref = goL ? w.q0.w : w.q2.y;
         geom = (goL ? w.q1.y : w.q2.w) >> 16;
@@ -474,6 +486,182 @@ RT_HD bool pair_any_hit(const DevScene& sc, const uint4* __restrict__ pairs, V3 
       fetch_child_ref<kShared>(pairs, stack[--sp], ref, geom);
     }
   }
+}
+
+
+// =============================================================================================
+// Streaming traversal: the per-lane state machine of wf_trace_kernel (wavefront.cuh), one step at a time.
+//
+// The kernel keeps one query per lane and advances it by ONE step per warp iteration: an inner-node step
+// (stream_trav: both child boxes of a pair record), a leaf step (stream_leaf: one primitive test) or the start of
+// the next query (stream_begin). The steps are written here, RT_HD, so that tests/host_pair_check.cpp runs the very
+// same code on the CPU against the oracle. Answers are those of CompactBvh::intersect (include/CompactBvh.hpp:80-139)
+// with the bounce loop's window tMin = 0, tMax = inf (trace.cpp:128-130); the visiting order is near-first as in
+// pair_closest_hit above.
+//
+// What keeps the steps short:
+//  * the node a lane holds is ONE word, the child reference itself (inner: kRefInner | pair, leaf: type << 30 | index,
+//    kRefNone: query finished), so descending is a select and the phase of a lane is a comparison;
+//  * deferred children are stacked as {reference, entry distance}; the top of the stack lives in two registers, so a
+//    pop is two moves plus a reload that nothing waits for;
+//  * geomID / primID of the winner are looked up once per query from leafInfo (by the shading kernel), equal-t ties
+//    compare the reference node indices stored there;
+//  * triangles of a NaN-free query (fast_query_ok) are tested by tri_test_fast on vertex copies whose components are
+//    already rotated for the ray's kz: no per-test permutation, no divergent min/max chains.
+
+// Index of a leaf reference's primitive in DevScene::leafInfo: triangles, then spheres, then discs.
+RT_HD uint32_t prim_slot(const DevScene& sc, uint32_t ref) {
+  const uint32_t type = ref >> 30, index = ref & kLeafIndexMask;
+  return index + (type == 0u ? 0u : (type == 1u ? sc.numTris : sc.numTris + sc.numSpheres));
+}
+
+RT_HD float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// TriangleMesh::intersectTriangle (src/Mesh.cpp:6-104) for the case in which no NaN can occur before the final
+// comparisons: triangle vertices, ray origin and the three shear constants all finite and below 2^20 in magnitude.
+// Then every translated/sheared coordinate is below 2^42 and every edge function below 2^85 (finite), so the
+// reference's Vec3fa::maxi()/operator[] chains over |values| -- which select the MINIMUM component, see rt_math.h --
+// equal fminf(fminf(a, b), c) (all inputs non-NaN and non-negative). Everything else is the statement sequence of
+// tri_test above. a, b, c are the triangle's vertices with their components already rotated by the ray's kz
+// (DevScene::triVerts copy kz + 1, or copy 0 for kz = 2) and op is the ray origin rotated the same way:
+// a - op == permute(p0 - o, kz) component by component. Returns t (0 = miss).
+RT_HD float tri_test_fast(V3 a, V3 b, V3 c, V3 op, float sx, float sy, float sz, float& b0, float& b1, float& b2) {
+  V3 p0t = a - op, p1t = b - op, p2t = c - op;
+  p0t.x += sx * p0t.z; p0t.y += sy * p0t.z;
+  p1t.x += sx * p1t.z; p1t.y += sy * p1t.z;
+  p2t.x += sx * p2t.z; p2t.y += sy * p2t.z;
+  const float e0 = p1t.x * p2t.y - p1t.y * p2t.x;
+  const float e1 = p2t.x * p0t.y - p2t.y * p0t.x;
+  const float e2 = p0t.x * p1t.y - p0t.y * p1t.x;
+  if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return 0.f;
+  const float det = e0 + e1 + e2;
+  if (det == 0) return 0.f;
+  p0t.z *= sz; p1t.z *= sz; p2t.z *= sz;
+  const float tScaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+  const float inf = __builtin_huge_valf();
+  if (det < 0.f && (tScaled >= 0.f || tScaled < inf * det)) return 0.f;
+  else if (det > 0.f && (tScaled <= 0.f || tScaled > inf * det)) return 0.f;
+  const float invDet = 1 / det;
+  b0 = e0 * invDet; b1 = e1 * invDet; b2 = e2 * invDet;
+  const float t = tScaled * invDet;
+  const float maxZt = min3f(fabsf(p0t.z), fabsf(p1t.z), fabsf(p2t.z));
+  const float deltaZ = kGamma3 * maxZt;
+  const float maxXt = min3f(fabsf(p0t.x), fabsf(p1t.x), fabsf(p2t.x));
+  const float maxYt = min3f(fabsf(p0t.y), fabsf(p1t.y), fabsf(p2t.y));
+  const float deltaX = kGamma5 * (maxXt + maxZt);
+  const float deltaY = kGamma5 * (maxYt + maxZt);
+  const float deltaE = 2 * (kGamma2 * maxXt * maxYt + deltaY * maxXt + deltaX * maxYt);
+  const float maxE = min3f(fabsf(e0), fabsf(e1), fabsf(e2));
+  const float deltaT = 3 * (kGamma3 * maxE * maxZt + deltaE * maxZt + deltaZ * maxE) * fabsf(invDet);
+  if (t <= deltaT) return 0.f;
+  return t;
+}
+
+constexpr float kFastBound = 1048576.f;  // 2^20, see tri_test_fast
+RT_HD bool below_bound(float x) { return fabsf(x) < kFastBound; }  // false for NaN and +-inf
+
+struct StreamQuery {
+  V3 o, d, inv;       // ray as given, 1/d
+  V3 op;              // origin rotated by kz (tri_test_fast)
+  float sx, sy, sz;   // RayShearParams (src/Primitives.cpp:5-22)
+  uint32_t permOfs;   // offset, in float4s, of the triangle-vertex copy rotated for this ray's kz
+  bool fast;          // no NaN can occur in this query's box and triangle tests: slab_fast / tri_test_fast apply
+  float hitT;         // closest t so far
+  uint32_t hitRef;    // leaf reference of the winner, kRefNone = nothing hit
+  float b0, b1, b2;   // barycentrics of the winning triangle
+  uint32_t ref;       // node held: inner (ref_is_inner), leaf (ref_is_leaf) or kRefNone = query finished
+  uint32_t topRef;    // top of the stack of deferred children, kept in registers
+  float topE;
+  int sp;             // entries below the top that live in `stack`
+};
+
+// Start of CompactBvh::intersect for the ray (o, d) with tMin = 0, tMax = inf: per-ray constants and the root test.
+// `stack` needs kMaxStack + 1 entries.
+RT_HD void stream_begin(const DevScene& sc, StreamQuery& q, V3 o, V3 d) {
+  q.o = o; q.d = d;
+  q.inv = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
+  const Shear sh = make_shear(d);
+  q.sx = sh.sx; q.sy = sh.sy; q.sz = sh.sz;
+  q.op = permute(o, sh.kz);
+  q.permOfs = (sh.kz == 2 ? 0u : (uint32_t)sh.kz + 1u) * sc.numTris * 3u;
+  q.fast = sc.boundsFinite != 0u && sc.trisBounded != 0u && is_finite_f(q.inv.x) && is_finite_f(q.inv.y) && is_finite_f(q.inv.z) &&
+           below_bound(o.x) && below_bound(o.y) && below_bound(o.z) && below_bound(q.sx) && below_bound(q.sy) && below_bound(q.sz);
+  q.hitT = __builtin_huge_valf(); q.hitRef = kRefNone; q.b0 = q.b1 = q.b2 = 0.f;
+  // bottom of the stack: popping it ends the query (its entry distance, -inf, is never beyond the closest hit)
+  q.topRef = kRefNone; q.topE = -__builtin_huge_valf(); q.sp = 1;
+  q.ref = root_slab(sc, o, q.inv, 0.f, q.hitT, q.fast) ? sc.rootRef : kRefNone;
+}
+
+// Next deferred child. Returns true when that child's entry distance lies beyond the closest hit (the reference's
+// pop-time slab test would reject it): the caller pops again.
+RT_HD bool stream_pop(StreamQuery& q, const uint2* stack) {
+  const float e = q.topE;
+  q.ref = q.topRef;
+  const uint2 below = stack[--q.sp];
+  q.topRef = below.x; q.topE = bits_f(below.y);
+  return e > q.hitT;
+}
+
+// One inner-node step on the pair record `w` of q.ref. Returns stream_pop's "pop again".
+RT_HD bool stream_trav(StreamQuery& q, const PairWords& w, uint2* stack) {
+  bool h0, h1;
+  float e0, e1;
+  if (q.fast) pair_slabs<true>(w, q.o, q.inv, 0.f, q.hitT, h0, h1, e0, e1);
+  else pair_slabs<false>(w, q.o, q.inv, 0.f, q.hitT, h0, h1, e0, e1);
+  const bool goL = h0 && (!h1 || !(e1 < e0));  // ties go to the first child, like pre-order
+  if (h0 && h1) {
+    stack[q.sp++] = make_uint2(q.topRef, f_bits(q.topE));
+    q.topRef = goL ? w.q2.y : w.q0.w;
+    q.topE = goL ? e1 : e0;
+  }
+  if (h0 || h1) {
+    q.ref = goL ? w.q0.w : w.q2.y;
+    return false;
+  }
+  return stream_pop(q, stack);
+}
+
+// One leaf step on q.ref: primitive test (primLookup + Primitive::intersect, codelets/TraceCodelets.cpp:127-140) and
+// the acceptance of CompactBvh.hpp:124 (0 < t < closest; an equal t replaces the winner only if this primitive's leaf
+// precedes the winner's in the reference's pre-order walk). Returns stream_pop's "pop again".
+RT_HD bool stream_leaf(const DevScene& sc, StreamQuery& q, const uint2* stack) {
+  const uint32_t type = q.ref >> 30, index = q.ref & kLeafIndexMask;
+  float t, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  if (type == 0u) {
+    if (q.fast) {
+      const float4* tv = sc.triVerts + (q.permOfs + 3u * index);
+      const float4 a = RT_LDG(tv), b = RT_LDG(tv + 1), c = RT_LDG(tv + 2);
+      t = tri_test_fast(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), q.op, q.sx, q.sy, q.sz, b0, b1, b2);
+    } else {
+      const float4* tv = sc.triVerts + 3u * index;
+      const float4 a = RT_LDG(tv), b = RT_LDG(tv + 1), c = RT_LDG(tv + 2);
+      Shear sh;
+      sh.kz = q.permOfs == 0u ? 2 : (q.permOfs == sc.numTris * 3u ? 0 : 1);
+      sh.sx = q.sx; sh.sy = q.sy; sh.sz = q.sz;
+      t = tri_test(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), q.o, sh, b0, b1, b2);
+    }
+    t = t > 0.f ? t : __builtin_huge_valf();  // Mesh.hpp:90-93: only t > 0 replaces the inf default
+  } else if (type == 1u) {
+    t = sphere_test(RT_LDG(sc.spheres + index), q.o, q.d, 0.f);
+  } else {
+    t = disc_test(sc.discs + 7u * index, q.o, q.d);
+  }
+  if (t > 0.f) {
+    bool accept = t < q.hitT;
+    if (!accept && t == q.hitT && q.hitRef != kRefNone)
+      accept = RT_LDG(&sc.leafInfo[prim_slot(sc, q.ref)].z) < RT_LDG(&sc.leafInfo[prim_slot(sc, q.hitRef)].z);
+    if (accept) { q.hitT = t; q.hitRef = q.ref; q.b0 = b0; q.b1 = b1; q.b2 = b2; }
+  }
+  return stream_pop(q, stack);
+}
+
+// geomID / primID / global triangle index of a finished query's winner, as the reference reports them.
+RT_HD void stream_hit_ids(const DevScene& sc, uint32_t hitRef, uint32_t& geomID, uint32_t& primID, uint32_t& tri) {
+  geomID = kInvalidGeom; primID = kInvalidPrim; tri = 0u;
+  if (hitRef == kRefNone) return;
+  const uint4 info = RT_LDG(sc.leafInfo + prim_slot(sc, hitRef));
+  geomID = info.x; primID = info.y;
+  tri = (hitRef >> 30) == 0u ? (hitRef & kLeafIndexMask) : 0u;
 }
 
 }  // namespace rt

@@ -14,7 +14,8 @@ namespace rt {
 
 struct SceneTables {
   std::vector<GeomEntry> geoms;
-  std::vector<float> triVerts;    // [num_tris][3][4]
+  std::vector<float> triVerts;    // [3][num_tris][3][4]: as given, then rotated for kz = 0 (y,z,x) and kz = 1 (z,x,y)
+  bool trisBounded = true;        // every vertex finite and below 2^20 in magnitude (tri_test_fast)
   std::vector<float> triNormals;  // same shape, empty when the scene has no normals
   PairTable pairs;
 };
@@ -46,7 +47,8 @@ inline std::string build_scene_tables(const b200rt_scene_desc& d, SceneTables& o
       return "unknown GeomType";
     }
   }
-  out.triVerts.assign((size_t)d.num_tris * 12, 0.f);
+  out.triVerts.assign((size_t)d.num_tris * 12 * 3, 0.f);
+  out.trisBounded = true;
   out.triNormals.clear();
   if (d.num_normals) out.triNormals.assign((size_t)d.num_tris * 12, 0.f);
   for (uint32_t m = 0; m < d.num_meshes; ++m) {
@@ -59,12 +61,20 @@ inline std::string build_scene_tables(const b200rt_scene_desc& d, SceneTables& o
         const uint32_t vi = tris[3 * gt + k];
         if (vi >= mi.numVertices) return "triangle index exceeds its mesh's vertex window";
         const size_t gv = (size_t)mi.firstVertex + vi;
-        std::memcpy(&out.triVerts[12 * gt + 4 * k], verts + 3 * gv, 12);
+        const float* v = verts + 3 * gv;
+        std::memcpy(&out.triVerts[12 * gt + 4 * k], v, 12);
+        float* r0 = &out.triVerts[12 * ((size_t)d.num_tris + gt) + 4 * k];      // permute(v, 0) = (y, z, x)
+        float* r1 = &out.triVerts[12 * (2 * (size_t)d.num_tris + gt) + 4 * k];  // permute(v, 1) = (z, x, y)
+        r0[0] = v[1]; r0[1] = v[2]; r0[2] = v[0];
+        r1[0] = v[2]; r1[1] = v[0]; r1[2] = v[1];
+        for (int c = 0; c < 3; ++c)
+          if (!(std::fabs(v[c]) < kFastBound)) out.trisBounded = false;
         if (d.num_normals) std::memcpy(&out.triNormals[12 * gt + 4 * k], normals + 3 * gv, 12);
       }
     }
   }
-  return build_pair_table(d.bvh_nodes, d.num_bvh_nodes, out.geoms.data(), d.num_geometry, primCount.data(), out.pairs);
+  return build_pair_table(d.bvh_nodes, d.num_bvh_nodes, out.geoms.data(), d.num_geometry, primCount.data(), d.num_tris,
+                          d.num_spheres, d.num_discs, out.pairs);
 }
 
 }  // namespace rt

@@ -31,7 +31,7 @@ struct WfBuffers {
   float4* thr;        // [P] throughput.xyz, w = tMax of the last intersect (HitRecord::r.tMax)
   uint4* rng;         // [P] xoroshiro state {s0.lo, s0.hi, s1.lo, s1.hi}
   float4* nrm;        // [P] normal.xyz; read and written only for paths of the last sample
-  float4* hitA;       // [P] t, geomID bits, primID bits, tri bits
+  float2* hitA;       // [P] closest t, leaf reference of the winner (kRefNone = no hit)
   float4* hitB;       // [P] b0, b1, b2; only when the scene interpolates normals (else null)
   uint32_t* queue[2];  // [P] path ids of the current / next bounce
   const uint32_t* traceOrder;  // optional: the current queue's path ids in the order wf_trace should take them (null = queue order)
@@ -65,24 +65,33 @@ __device__ __forceinline__ void wf_camera_path(const WfArgs& a, uint32_t p, V3& 
 
 // ------------------------------------------------------------------------------------------------
 // wf_trace: one closest-hit query per path of the bounce's queue (CompactBvh::intersect, include/CompactBvh.hpp:80-139,
-// near-first order over the pair table of rt_prims.h).
+// near-first order over the pair table; the steps themselves are rt_prims.h "Streaming traversal").
 //
 // Persistent 1024-thread CTAs, the pair table staged in shared memory when it fits. Every lane owns one query at a
-// time and is in one of three phases: TRAV (it holds an inner node: load its 48-byte pair record, test both child
-// boxes, descend / defer / pop), LEAF (it holds a leaf: run the primitive test, then pop) or FETCH (its query is
-// finished: store the hit, take the next ray of the warp's batch, test the root). A warp iteration executes ONE
+// time and is in one of three phases, told apart by the node reference it holds: TRAV (an inner node: load its 48-byte
+// pair record, test both child boxes, descend / defer / pop), LEAF (a leaf: run the primitive test, then pop) or FETCH
+// (query finished: store the hit, take the next ray of the warp's batch, test the root). A warp iteration executes ONE
 // phase, chosen by ballot: inner-node steps as long as at least `travThreshold` lanes want one (a single ballot on
 // that path), otherwise whichever phase most lanes wait for. Lanes therefore never wait for a neighbour's long
 // traversal, only for their phase to be scheduled.
-enum : uint32_t { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2, WF_DONE = 3 };
+enum : uint32_t { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2 };
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 
 template <bool kShared, bool kCount, bool kFirst>
 __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const uint4* pairs = stage_pairs<kShared>(a.t, reinterpret_cast<uint4*>(smemRaw));
+  // Shared-window address of the staged table, made opaque to the compiler: sm_100 materialises a shared symbol's
+  // address as (CTA rank in cluster << 24 | offset) with an S2R, and would redo that in every inner-node step.
+  uint32_t pairsShared = kShared ? (uint32_t)__cvta_generic_to_shared(smemRaw) : 0u;
+  asm volatile("" : "+r"(pairsShared));
   const DevScene& sc = a.t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
-  const float inf = __int_as_float(0x7f800000);
   // bounce 0 (kFirst): the queue is the identity over all paths of the chunk and the rays are the camera rays
   const uint32_t* queue = a.b.traceOrder ? a.b.traceOrder : a.b.queue[a.qIn];
   const uint32_t count = kFirst ? a.numPaths : a.b.counts[a.qIn];
@@ -90,49 +99,29 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   Counters cnt = {0u, 0u};
   unsigned nClosest = 0;
 
-  // the lane's query
-  V3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 0.f, -1.f), inv = mk(0.f, 0.f, 0.f);
-  Shear sh;
-  sh.kz = 2; sh.sx = sh.sy = sh.sz = 0.f;
-  PairHit hit;
-  hit.t = inf; hit.geomID = kInvalidGeom; hit.ref = 0u; hit.key = 0u; hit.b0 = hit.b1 = hit.b2 = 0.f;
-  uint32_t ref = 0u;       // TRAV: pair index of the inner node held; LEAF: leaf reference held
-  uint32_t geom = 0u;      // LEAF: geomID of the leaf held
-  uint32_t key = 0u;       // LEAF: pair * 2 + side of the leaf held
-  uint32_t path = 0xFFFFFFFFu;
-  bool fast = true;        // the query may use the NaN-free slab test (fast_slab_ok)
-  uint2 stack[kMaxStack];  // deferred children: {key, entry distance}
-  int sp = 0;
-  uint32_t phase = WF_FETCH;
+  StreamQuery q;  // the lane's query
+  q.o = q.op = q.inv = mk(0.f, 0.f, 0.f); q.d = mk(0.f, 0.f, -1.f);
+  q.sx = q.sy = q.sz = 0.f; q.permOfs = 0u; q.fast = true;
+  q.hitT = __int_as_float(0x7f800000); q.hitRef = kRefNone; q.b0 = q.b1 = q.b2 = 0.f;
+  q.ref = kRefNone; q.topRef = kRefNone; q.topE = 0.f; q.sp = 1;
+  uint32_t path = 0xFFFFFFFFu;  // the path whose query this is; none before the first fetch
+  uint2 stack[kMaxStack + 1];   // deferred children below the register-held top: {reference, entry distance}
   // ray ids are claimed from the bounce's queue kClaim at a time per warp: one same-address atomic per 128 rays
   constexpr uint32_t kClaim = 128;
   uint32_t wNext = 0, wEnd = 0;  // warp-uniform: the unclaimed part of this warp's current batch
   unsigned phaseIters[3] = {0u, 0u, 0u}, phaseLanes[3] = {0u, 0u, 0u};  // kCount builds: scheduler statistics
 
-  // next deferred child that can still hold a closer hit (the reference's pop-time slab test), or the end of the query
-  auto pop_next = [&]() {
-    bool found = false;
-    uint2 e = make_uint2(0u, 0u);
-    while (sp > 0) {
-      e = stack[--sp];
-      if (!(__uint_as_float(e.y) > hit.t)) { found = true; break; }
-    }
-    if (!found) { phase = WF_FETCH; return; }
-    key = e.x;
-    fetch_child_ref<kShared>(pairs, key, ref, geom);
-    phase = geom != kInvalidGeom ? WF_LEAF : WF_TRAV;
-  };
-
   while (true) {
-    const unsigned mT = __ballot_sync(full, phase == WF_TRAV);
+    const bool wantT = ref_is_inner(q.ref);
+    const unsigned mT = __ballot_sync(full, wantT);
     const int cT = __popc(mT);
     uint32_t pick = WF_TRAV;
     unsigned mF = 0u;
     int cF = 0, cL = 0;
     if (cT < a.travThreshold) {
-      const unsigned mL = __ballot_sync(full, phase == WF_LEAF);
-      mF = __ballot_sync(full, phase == WF_FETCH);
-      if (!(mT | mL | mF)) break;
+      const unsigned mL = __ballot_sync(full, ref_is_leaf(q.ref));
+      mF = __ballot_sync(full, q.ref == kRefNone);
+      if (!(mT | mL | mF)) break;  // every lane is kRefDone
       cL = __popc(mL); cF = __popc(mF);
       if (!(cT >= cL && cT >= cF)) pick = cL >= cF ? WF_LEAF : WF_FETCH;
     }
@@ -141,35 +130,24 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
       phaseLanes[pick] += (unsigned)(pick == WF_TRAV ? cT : (pick == WF_LEAF ? cL : cF));
     }
 
+    bool again = false;  // the node just popped is culled: keep popping
     if (pick == WF_TRAV) {
-      if (phase == WF_TRAV) {
-        const PairWords w = fetch_pair<kShared>(pairs, ref);
-        if (kCount) cnt.nodeVisits += 2;
-        bool h0, h1;
-        float e0, e1;
-        if (fast) pair_slabs<true>(w, o, inv, 0.f, hit.t, h0, h1, e0, e1);
-        else pair_slabs<false>(w, o, inv, 0.f, hit.t, h0, h1, e0, e1);
-        if (h0 | h1) {
-          const bool goL = h0 && (!h1 || !(e1 < e0));  // ties go to the first child, like pre-order
-          const uint32_t k0 = ref * 2u;
-          if (h0 && h1) stack[sp++] = make_uint2(goL ? k0 + 1u : k0, __float_as_uint(goL ? e1 : e0));
-          geom = (goL ? w.q1.y : w.q2.w) >> 16;
-          key = goL ? k0 : k0 + 1u;
-          ref = goL ? w.q0.w : w.q2.y;
-          if (geom != kInvalidGeom) phase = WF_LEAF;
+      if (wantT) {
+        PairWords w;
+        if (kShared) {
+          // (kRefInner | pair) * 48 wraps to pair * 48 in 32 bits: the reference needs no mask
+          const uint32_t at = pairsShared + q.ref * 48u;
+          w.q0 = lds128(at); w.q1 = lds128(at + 16u); w.q2 = lds128(at + 32u);
         } else {
-          pop_next();
+          w = fetch_pair<false>(pairs, ref_pair(q.ref));
         }
+        if (kCount) cnt.nodeVisits += 2;
+        again = stream_trav(q, w, stack);
       }
     } else if (pick == WF_LEAF) {
-      if (phase == WF_LEAF) {
+      if (ref_is_leaf(q.ref)) {
         if (kCount) cnt.primTests++;
-        float b0, b1, b2;
-        const float t = leaf_eval(sc, ref, o, d, 0.f, sh, b0, b1, b2);
-        if (accept_hit(sc, t, 0.f, hit, key)) {
-          hit.t = t; hit.geomID = geom; hit.ref = ref; hit.key = key; hit.b0 = b0; hit.b1 = b1; hit.b2 = b2;
-        }
-        pop_next();
+        again = stream_leaf(sc, q, stack);
       }
     } else {
       // lanes that finished a query store its result and take the next ray ids of the warp's batch
@@ -181,20 +159,20 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
       }
       const uint32_t avail = wEnd - wNext;
       const uint32_t rank = (uint32_t)__popc(mF & ((1u << lane) - 1u));
-      const bool served = phase == WF_FETCH && rank < avail;  // the others retry on the next fetch step
+      const bool served = q.ref == kRefNone && rank < avail;  // the others retry on the next fetch step
       const uint32_t qi = wNext + rank;
       wNext += min((uint32_t)cF, avail);
       if (served) {
         if (path != 0xFFFFFFFFu) {
-          uint32_t primID, tri;
-          hit_ids(sc, hit, primID, tri);
-          a.b.hitA[path] = make_float4(hit.t, __uint_as_float(hit.geomID), __uint_as_float(primID), __uint_as_float(tri));
-          if (a.b.hitB) a.b.hitB[path] = make_float4(hit.b0, hit.b1, hit.b2, 0.f);
+          // the shading kernel turns the winner's leaf reference into geomID / primID (stream_hit_ids)
+          a.b.hitA[path] = make_float2(q.hitT, __uint_as_float(q.hitRef));
+          if (a.b.hitB) a.b.hitB[path] = make_float4(q.b0, q.b1, q.b2, 0.f);
           path = 0xFFFFFFFFu;
         }
         if (qi >= count) {
-          phase = WF_DONE;
+          q.ref = kRefDone;
         } else {
+          V3 o, d;
           if (kFirst) {
             path = qi;
             Rng unused;
@@ -205,23 +183,15 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
             o = mk(ro.x, ro.y, ro.z);
             d = mk(rd.x, rd.y, rd.z);
           }
-          // start of CompactBvh::intersect (tMin = 0, tMax = inf as set by the bounce loop, trace.cpp:128-130)
+          // start of CompactBvh::intersect (tMin = 0, tMax = inf as set by the bounce loop, trace.cpp:128-130); a ray
+          // that misses the root holds kRefNone again: its (empty) result is stored on the next fetch step
           nClosest++;
-          inv = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
-          sh = make_shear(d);
-          fast = fast_slab_ok(sc, o, inv, 0.f, inf);
-          hit.t = inf; hit.geomID = kInvalidGeom; hit.ref = 0u; hit.key = 0u; hit.b0 = hit.b1 = hit.b2 = 0.f;
-          sp = 0;
           if (kCount) cnt.nodeVisits++;
-          if (!root_slab(sc, o, inv, 0.f, inf, fast)) {
-            phase = WF_FETCH;  // missed the scene: the result (no hit) is stored on the next fetch step
-          } else {
-            ref = sc.rootRef; geom = sc.rootGeom; key = 0u;
-            phase = geom != kInvalidGeom ? WF_LEAF : WF_TRAV;
-          }
+          stream_begin(sc, q, o, d);
         }
       }
     }
+    while (again) again = stream_pop(q, stack);
   }
   if (kCount && a.phaseStats && lane == 0)
     for (int k = 0; k < 3; ++k) { atomicAdd(a.phaseStats + 2 * k, (unsigned long long)phaseIters[k]); atomicAdd(a.phaseStats + 2 * k + 1, (unsigned long long)phaseLanes[k]); }
@@ -251,9 +221,10 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
     uint32_t appendSlot = 0xFFFFFFFFu, p = 0;
     if (valid) {
       p = kFirst ? i : queueIn[i];
-      const float4 ha = a.b.hitA[p];
+      const float2 ha = a.b.hitA[p];
       Hit hit;
-      hit.t = ha.x; hit.geomID = __float_as_uint(ha.y); hit.primID = __float_as_uint(ha.z); hit.tri = __float_as_uint(ha.w);
+      hit.t = ha.x;
+      stream_hit_ids(sc, __float_as_uint(ha.y), hit.geomID, hit.primID, hit.tri);
       hit.node = 0; hit.b0 = hit.b1 = hit.b2 = 0.f;
       if (a.b.hitB) { const float4 hb = a.b.hitB[p]; hit.b0 = hb.x; hit.b1 = hb.y; hit.b2 = hb.z; }
       const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;

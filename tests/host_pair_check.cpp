@@ -36,6 +36,10 @@ bool make_view(const b200rt_scene_desc* d, HostView& v) {
   s.rootRef = v.tables.pairs.rootRef;
   s.rootGeom = v.tables.pairs.rootGeom;
   s.boundsFinite = v.tables.pairs.boundsFinite ? 1u : 0u;
+  s.leafInfo = (const uint4*)v.tables.pairs.leafInfo.data();
+  s.numTris = d->num_tris;
+  s.numSpheres = d->num_spheres;
+  s.trisBounded = v.tables.trisBounded ? 1u : 0u;
   return true;
 }
 }  // namespace
@@ -69,6 +73,47 @@ int hostpair_intersect(const b200rt_scene_desc* d, const void* raysIn, size_t n,
       q.normal[0] = nn.x; q.normal[1] = nn.y; q.normal[2] = nn.z;
     }
     out[i] = q;
+  }
+  if (counters) { counters[0] = nv; counters[1] = np; counters[2] = nf; }
+  return 0;
+}
+
+// The per-lane state machine of wf_trace_kernel (stream_begin / stream_trav / stream_leaf / stream_pop), one query at a
+// time, tMin = 0 and tMax = inf. counters: [0] node visits, [1] primitive tests, [2] queries on the NaN-free fast path.
+int hostpair_stream_intersect(const b200rt_scene_desc* d, const void* raysIn, size_t n, b200rt_hit* out, uint64_t* counters) {
+  HostView v;
+  if (!make_view(d, v)) return -1;
+  const float* rays = (const float*)raysIn;
+  uint64_t nv = 0, np = 0, nf = 0;
+  std::vector<uint2> stack(rt::kMaxStack + 1, make_uint2(0u, 0u));
+  for (size_t i = 0; i < n; ++i) {
+    const float* r = rays + 8 * i;
+    const rt::V3 o = rt::mk(r[0], r[1], r[2]), dir = rt::mk(r[4], r[5], r[6]);
+    rt::StreamQuery q;
+    rt::stream_begin(v.dev, q, o, dir);
+    nv += 1;
+    nf += q.fast ? 1 : 0;
+    while (q.ref != rt::kRefNone) {
+      bool again;
+      if (rt::ref_is_inner(q.ref)) {
+        nv += 2;
+        again = rt::stream_trav(q, rt::fetch_pair<false>(v.dev.pairs, rt::ref_pair(q.ref)), stack.data());
+      } else {
+        np += 1;
+        again = rt::stream_leaf(v.dev, q, stack.data());
+      }
+      while (again) again = rt::stream_pop(q, stack.data());
+    }
+    b200rt_hit h;
+    uint32_t tri;
+    h.t = q.hitT;
+    rt::stream_hit_ids(v.dev, q.hitRef, h.geom_id, h.prim_id, tri);
+    h.normal[0] = h.normal[1] = h.normal[2] = 0.f;
+    if (h.geom_id != rt::kInvalidGeom) {
+      const rt::V3 nn = rt::prim_normal(v.dev, h.geom_id, tri, q.b0, q.b1, q.b2, o + dir * q.hitT);
+      h.normal[0] = nn.x; h.normal[1] = nn.y; h.normal[2] = nn.z;
+    }
+    out[i] = h;
   }
   if (counters) { counters[0] = nv; counters[1] = np; counters[2] = nf; }
   return 0;

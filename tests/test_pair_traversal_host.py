@@ -24,15 +24,22 @@ def hostpair():
     L = C.CDLL(str(LIB))
     L.hostpair_last_error.restype = C.c_char_p
     L.hostpair_intersect.argtypes = [C.POINTER(capi.SceneDesc), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.hostpair_stream_intersect.argtypes = L.hostpair_intersect.argtypes
     L.hostpair_occluded.argtypes = [C.POINTER(capi.SceneDesc), C.c_void_p, C.c_size_t, C.c_void_p]
     L.hostpair_validate.argtypes = [C.POINTER(capi.SceneDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
-def run_intersect(L, s, rays):
+# "pair": pair_closest_hit (shadow / bare-query kernels); "stream": the step functions of wf_trace_kernel
+# (stream_begin / stream_trav / stream_leaf / stream_pop; window tMin = 0, tMax = inf as in the bounce loop)
+KINDS = ["pair", "stream"]
+
+
+def run_intersect(L, s, rays, kind="pair"):
     out = np.zeros(rays.size, dtype=capi.HIT)
     cnt = np.zeros(4, dtype=np.uint64)
-    assert L.hostpair_intersect(C.byref(s.desc), capi.ptr(rays), rays.size, capi.ptr(out), capi.ptr(cnt)) == 0, L.hostpair_last_error()
+    fn = L.hostpair_intersect if kind == "pair" else L.hostpair_stream_intersect
+    assert fn(C.byref(s.desc), capi.ptr(rays), rays.size, capi.ptr(out), capi.ptr(cnt)) == 0, L.hostpair_last_error()
     return out, cnt
 
 
@@ -51,19 +58,21 @@ def random_rays(n, seed, lo, hi, unit=True):
     return make_rays(o, d.astype(np.float32))
 
 
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("name", ["box", "spheres", "box-simple"])
-def test_closest_hit_matches_oracle_on_random_unit_rays(hostpair, port, name):
+def test_closest_hit_matches_oracle_on_random_unit_rays(hostpair, port, name, kind):
     s = scene.HostScene.builtin(name)
     mn, ext = root_box(s)
     rays = random_rays(60000, 7, mn - 0.1 * ext, mn + 1.1 * ext)
-    got, cnt = run_intersect(hostpair, s, rays)
+    got, cnt = run_intersect(hostpair, s, rays, kind)
     want, _ = port.intersect(s, rays)
     assert got.tobytes() == want.tobytes()
     assert cnt[2] == rays.size  # every one of these queries is NaN-free: the fast slab test was used
     assert (got["geom_id"] != capi.INVALID_GEOM).mean() > 0.1
 
 
-def test_camera_and_axis_aligned_rays(hostpair, port, box_scene):
+@pytest.mark.parametrize("kind", KINDS)
+def test_camera_and_axis_aligned_rays(hostpair, port, box_scene, kind):
     """Camera rays of the shadow-trace configuration include exact zeros in the direction (the centre column/row):
     those queries must take the NaN-preserving slab test and still agree bit for bit."""
     w = h = 128
@@ -74,13 +83,14 @@ def test_camera_and_axis_aligned_rays(hostpair, port, box_scene):
     axis = make_rays(np.tile(np.array([[0, 0, 0], [10, 20, -300], [0, 0, -500]], np.float32), (6, 1))[:18],
                      np.repeat(np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32), 3, axis=0))
     rays = np.concatenate([rays, axis])
-    got, cnt = run_intersect(hostpair, box_scene, rays)
+    got, cnt = run_intersect(hostpair, box_scene, rays, kind)
     want, _ = port.intersect(box_scene, rays)
     assert got.tobytes() == want.tobytes()
     assert 0 < cnt[2] < rays.size
 
 
-def test_rays_starting_on_node_planes_with_zero_direction_components(hostpair, port, box_scene):
+@pytest.mark.parametrize("kind", KINDS)
+def test_rays_starting_on_node_planes_with_zero_direction_components(hostpair, port, box_scene, kind):
     """(bound - origin) * (1/0) = NaN: the case the fast slab test must never see."""
     nodes = box_scene.bvh_nodes
     rng = np.random.default_rng(3)
@@ -90,7 +100,7 @@ def test_rays_starting_on_node_planes_with_zero_direction_components(hostpair, p
     d[np.arange(pick.size), rng.integers(0, 3, pick.size)] = 0.0
     d[::7] *= -0.0  # negative zeros too
     rays = make_rays(o, d)
-    got, cnt = run_intersect(hostpair, box_scene, rays)
+    got, cnt = run_intersect(hostpair, box_scene, rays, kind)
     want, _ = port.intersect(box_scene, rays)
     assert cnt[2] == 0
     # These rays are built to graze: they start ON a box corner, so some hit a shared triangle edge with bit-equal t in
@@ -103,12 +113,13 @@ def test_rays_starting_on_node_planes_with_zero_direction_components(hostpair, p
     assert got[same].tobytes() == want[same].tobytes()
 
 
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("fixture", ["dae_scene", "hdri_scene"])
-def test_imported_scenes(hostpair, port, fixture, request):
+def test_imported_scenes(hostpair, port, fixture, request, kind):
     s = request.getfixturevalue(fixture)
     mn, ext = root_box(s)
     rays = random_rays(40000, 11, mn - 0.2 * ext, mn + 1.2 * ext)
-    got, _ = run_intersect(hostpair, s, rays)
+    got, _ = run_intersect(hostpair, s, rays, kind)
     want, _ = port.intersect(s, rays)
     assert got.tobytes() == want.tobytes()
 
@@ -123,10 +134,11 @@ def test_any_hit_matches_oracle(hostpair, port, box_scene):
     assert np.array_equal(out, want) and 0.1 < out.mean() < 0.9
 
 
-def test_single_leaf_tree_and_equal_t_ties(hostpair, port):
+@pytest.mark.parametrize("kind", KINDS)
+def test_single_leaf_tree_and_equal_t_ties(hostpair, port, kind):
     one = CustomScene(spheres=[(0, 0, -5, 1)])
     rays = make_rays([[0, 0, 0], [0, 3, 0]], [[0, 0, -1], [0, 0, -1]])
-    got, _ = run_intersect(hostpair, one, rays)
+    got, _ = run_intersect(hostpair, one, rays, kind)
     want, _ = port.intersect(one, rays)
     assert got.tobytes() == want.tobytes() and got["geom_id"][0] == 0
     # two coincident quads: every hit is an exact tie between two leaves
@@ -134,7 +146,7 @@ def test_single_leaf_tree_and_equal_t_ties(hostpair, port):
     tie = CustomScene(meshes=[(q, [[0, 1, 2], [0, 2, 3]]), (q, [[0, 1, 2], [0, 2, 3]])])
     rng = np.random.default_rng(0)
     rays = make_rays(np.zeros((3000, 3), np.float32), np.c_[rng.uniform(-.3, .3, (3000, 2)), -np.ones(3000)].astype(np.float32))
-    got, _ = run_intersect(hostpair, tie, rays)
+    got, _ = run_intersect(hostpair, tie, rays, kind)
     want, _ = port.intersect(tie, rays)
     assert got.tobytes() == want.tobytes() and (got["geom_id"] != capi.INVALID_GEOM).mean() > 0.5
 
