@@ -47,12 +47,6 @@ tests/libhostpair.so: tests/host_pair_check.cpp $(CSRC)/rt_prims.h $(CSRC)/pair_
                       $(CSRC)/sin_deg_table.inc include/b200rt.h
 	$(CXX) $(HOSTFLAGS) -I/usr/local/cuda/include -shared -o $@ $<
 
-# Experiment build: adds a CUB-sorted ray order for wf_trace (B200RT_SORT=1) to measure what coherence is worth.
-# Never part of `all`; the product library carries no library kernels.
-experiments:
-	$(NVCC) $(NVFLAGS) -DB200RT_EXPERIMENT_SORT -c -o $(CSRC)/b200rt_exp.o $(CSRC)/b200rt.cu
-	$(NVCC) $(ARCH) -shared -ccbin $(CXX) -o $(PKG)/libb200rt_exp.so $(CSRC)/b200rt_exp.o $(CSRC)/nif.o -cudart static
-
 sass: $(PKG)/libb200rt.so
 	/usr/local/cuda/bin/cuobjdump -sass $(PKG)/libb200rt.so > /tmp/b200rt.sass
 
@@ -60,4 +54,4 @@ clean:
 	rm -f $(CSRC)/*.o $(PKG)/*.so $(PKG)/trace
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean sass experiments
+.PHONY: all oracle clean sass

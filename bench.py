@@ -538,11 +538,14 @@ def rooflines(prof, peaks, n_local, spp, flops_per_lookup, sm_mhz=None, shadow=F
              "frac": nif_flops / nif_s / 1e12 / peaks["bf16_tflops_sustained"] if nif_flops else 0.0,
              "traffic": (traffic.get("nif_mlp_kernel") or {}).get("dram_bytes_per_step"), "traffic_unit": unit_note})
     if wavefront:
-        # wf_shade: HBM-bound on the path record. Algorithmic bytes per path-bounce: 84 B read (queue id, hit, origin,
-        # direction, throughput, RNG; only the 16 B hit at bounce 0, whose camera ray is recomputed) + 68 B written for
-        # the ~70 % that survive (+ the 12 B colour slot at bounce 0).
+        # wf_shade: HBM-bound on the path record (dense, slot-indexed). Algorithmic bytes: every bounce query beyond a
+        # path's first (queries - samples of them; each is also exactly one survivor of the previous bounce) reads 72 B
+        # (8 B hit + origin, direction, throughput, RNG) and was written as a 96 B record (+ 1/d and shear constants of
+        # the next query); every camera path reads its 8 B hit and writes the 12 B colour slot; every path ends once
+        # with a 20 B throughput / escape record.
         shade_s = max(prof["shade_kernel_ms"] * 1e-3, 1e-9)
-        shade_bytes = (prof["queries"] - prof["samples"]) * 84.0 + prof["samples"] * (16.0 + 12.0) + prof["queries"] * 0.7 * 68.0
+        bounce_q = prof["queries"] - prof["samples"]
+        shade_bytes = bounce_q * (72.0 + 96.0) + prof["samples"] * (8.0 + 12.0 + 20.0)
         sl = max(prof["shade_kernel_launches"], 1)
         kernels.append({"kernel": "wf_shade_kernel", "bound": "hbm", "share_of_step": shade_s / step_s,
                         "launches_per_step": prof["shade_kernel_launches"], "avg_launch_ms": shade_s * 1e3 / sl,

@@ -18,9 +18,6 @@
 #include "../../include/b200rt.h"
 #include "nif.cuh"
 #include "scene_tables.hpp"
-#ifdef B200RT_EXPERIMENT_SORT
-#include <cub/device/device_radix_sort.cuh>
-#endif
 #include "trace_kernels.cuh"
 #include "wavefront.cuh"
 
@@ -88,7 +85,7 @@ struct b200rt_scene {
   DeviceBuffer workCounter, counters, primA, primB;
   DeviceBuffer rays;                                   // device copy of the stream (host-buffer entry point)
   DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
-  DeviceBuffer wfRayO, wfRayD, wfNrm, wfThr, wfRng, wfHitA, wfHitB, wfQ0, wfQ1, wfCounts;  // wavefront path state
+  DeviceBuffer wfState[2][7], wfHitA, wfHitB, wfCounts;  // wavefront path state (two slot-indexed arrays of records)
   b200rt_trace_stats stats{};
   float hdriRotationDegrees = 0.f;
   float rootBox[6] = {0.f, 0.f, 0.f, 1.f, 1.f, 1.f};  // min, extent of the root node
@@ -100,9 +97,10 @@ struct b200rt_scene {
     if (nif) rt::nif_destroy(nif);
     for (DeviceBuffer* b : {&nodes, &pairs, &leafOrig, &leafInfo, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
                             &workCounter, &counters, &primA, &primB, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
-                            &escapeCount, &wfRayO, &wfRayD, &wfNrm, &wfThr, &wfRng, &wfHitA, &wfHitB, &wfQ0, &wfQ1,
-                            &wfCounts})
+                            &escapeCount, &wfHitA, &wfHitB, &wfCounts})
       b->release();
+    for (auto& set : wfState)
+      for (DeviceBuffer& b : set) b.release();
     if (evStart) cudaEventDestroy(evStart);
     if (evStop) cudaEventDestroy(evStop);
     if (stream) cudaStreamDestroy(stream);
@@ -353,13 +351,13 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
         chunk = 32u;
         while (chunk < 1024u && (size_t)chunk * 2 * n <= ((size_t)64 << 20)) chunk *= 2;
       }
-      // bound the per-path arrays (slots; plus 136 B of path state in wavefront mode) to ~8 / ~20 GiB
+      // bound the per-path arrays (slots; plus 2 x 112 B of path state + 24 B of hit in wavefront mode) to ~8 / ~24 GiB
       const bool slots = sc.nif || wavefront;  // per-sample colour / escape records handed to NIF + accumulate
       const bool primB = primaryPass && sc.dev.triNormals != nullptr;
-      const size_t perSlot = (slots ? (3 + 5 + 3 + 1) * sizeof(float) : 0) + (wavefront ? 120 : 0) +
+      const size_t perSlot = (slots ? (3 + 5 + 3 + 1) * sizeof(float) : 0) + (wavefront ? 248 : 0) +
                              (primaryPass ? (primB ? 32 : 16) : 0);
       static const size_t envBudget = [] { const char* e = std::getenv("B200RT_CHUNK_GIB"); return e ? (size_t)std::atoi(e) : (size_t)0; }();
-      const size_t budget = envBudget ? envBudget << 30 : (wavefront ? (size_t)20 << 30 : (size_t)8 << 30);
+      const size_t budget = envBudget ? envBudget << 30 : (wavefront ? (size_t)24 << 30 : (size_t)8 << 30);
       while (chunk > 1 && (size_t)chunk * n * perSlot > budget) chunk /= 2;
       if (chunk > count) chunk = count ? count : 1;
       if ((size_t)chunk * n > 0xFFFFFFF0ull) return fail(B200RT_ERR_UNSUPPORTED, "ray stream too long for one chunk");
@@ -384,17 +382,18 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
       rt::WfArgs w{};
       if (wavefront) {
         if (sc.desc.max_path_length > 255) return fail(B200RT_ERR_UNSUPPORTED, "wavefront path tracer: max_path_length > 255");
-        for (DeviceBuffer* b : {&sc.wfRayO, &sc.wfRayD, &sc.wfNrm, &sc.wfThr, &sc.wfRng, &sc.wfHitA})
-          CU_TRY(b->reserve(P * 16));
         const bool needBary = sc.dev.triNormals != nullptr;  // barycentrics only feed interpolated normals
+        for (int k = 0; k < 2; ++k) {
+          for (DeviceBuffer& b : sc.wfState[k]) CU_TRY(b.reserve(P * 16));
+          rt::WfState& st = w.b.st[k];
+          st.rayO = (float4*)sc.wfState[k][0].p; st.rayD = (float4*)sc.wfState[k][1].p; st.rayI = (float4*)sc.wfState[k][2].p;
+          st.rayS = (float4*)sc.wfState[k][3].p; st.thr = (float4*)sc.wfState[k][4].p; st.rng = (uint4*)sc.wfState[k][5].p;
+          st.nrm = (float4*)sc.wfState[k][6].p;
+        }
+        CU_TRY(sc.wfHitA.reserve(P * 8));
         if (needBary) CU_TRY(sc.wfHitB.reserve(P * 16));
-        CU_TRY(sc.wfQ0.reserve(P * 4));
-        CU_TRY(sc.wfQ1.reserve(P * 4));
         CU_TRY(sc.wfCounts.reserve(16));
-        w.b.rayO = (float4*)sc.wfRayO.p; w.b.rayD = (float4*)sc.wfRayD.p; w.b.nrm = (float4*)sc.wfNrm.p;
-        w.b.thr = (float4*)sc.wfThr.p; w.b.rng = (uint4*)sc.wfRng.p;
         w.b.hitA = (float2*)sc.wfHitA.p; w.b.hitB = needBary ? (float4*)sc.wfHitB.p : nullptr;
-        w.b.queue[0] = (uint32_t*)sc.wfQ0.p; w.b.queue[1] = (uint32_t*)sc.wfQ1.p;
         w.b.counts = (uint32_t*)sc.wfCounts.p;
         w.lastSample = first + count - 1;
         static const int envWf = [] { const char* e = std::getenv("B200RT_WF_THRESHOLD"); return e ? std::atoi(e) : 8; }();
@@ -428,31 +427,9 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
           for (uint32_t b = 0; b < sc.desc.max_path_length; ++b) {
             w.qIn = (int)(b & 1u);
             w.phaseStats = dPhase ? dPhase + 6 * std::min<uint32_t>(b, 15u) : nullptr;
-            CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + 2, 0, 4, sc.stream));            // fetch cursor
-            CU_TRY(cudaMemsetAsync((uint32_t*)sc.wfCounts.p + (w.qIn ^ 1), 0, 4, sc.stream));  // next queue size
-            const bool first = b == 0;  // bounce 0: camera rays are generated in the kernels, the queue is the identity
-            w.b.traceOrder = nullptr;
-#ifdef B200RT_EXPERIMENT_SORT
-            static const int envSort = [] { const char* e = std::getenv("B200RT_SORT"); return e ? std::atoi(e) : 0; }();
-            if (envSort && !first) {
-              // EXPERIMENT: wf_trace takes the bounce's rays sorted by (origin cell, direction bin); CUB radix sort
-              static DeviceBuffer keysIn, keysOut, idsIn, idsOut, tmp;
-              const size_t P = w.numPaths;
-              CU_TRY(keysIn.reserve(P * 4)); CU_TRY(keysOut.reserve(P * 4)); CU_TRY(idsIn.reserve(P * 4)); CU_TRY(idsOut.reserve(P * 4));
-              size_t tmpBytes = 0;
-              cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (uint32_t*)keysIn.p, (uint32_t*)keysOut.p, (uint32_t*)idsIn.p,
-                                              (uint32_t*)idsOut.p, (int)P, 0, 21, sc.stream);
-              CU_TRY(tmp.reserve(tmpBytes));
-              const float* root = sc.rootBox;
-              timer.begin(KernelTimer::ACCUM, sc.stream);  // booked under "accumulate" in the experiment
-              rt::wf_sort_key_kernel<<<sc.numSMs * 8, 256, 0, sc.stream>>>(w, (uint32_t*)keysIn.p, (uint32_t*)idsIn.p,
-                  make_float3(root[0], root[1], root[2]), make_float3(1.f / root[3], 1.f / root[4], 1.f / root[5]));
-              cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, (uint32_t*)keysIn.p, (uint32_t*)keysOut.p, (uint32_t*)idsIn.p,
-                                              (uint32_t*)idsOut.p, (int)P, 0, 21, sc.stream);
-              timer.end(sc.stream);
-              w.b.traceOrder = (const uint32_t*)idsOut.p;
-            }
-#endif
+            // no memsets between the kernels: wf_trace empties the counter its wf_shade appends to, wf_shade resets the
+            // fetch cursor of the next wf_trace
+            const bool first = b == 0;  // bounce 0: camera rays are generated in the kernels, slot = path
             timer.begin(KernelTimer::TRACE, sc.stream);
             {
               cudaError_t e;

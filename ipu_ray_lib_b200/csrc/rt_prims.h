@@ -561,7 +561,7 @@ constexpr float kFastBound = 1048576.f;  // 2^20, see tri_test_fast
 RT_HD bool below_bound(float x) { return fabsf(x) < kFastBound; }  // false for NaN and +-inf
 
 struct StreamQuery {
-  V3 o, d, inv;       // ray as given, 1/d
+  V3 o, d, inv;       // ray as given (d only where the caller keeps it, see stream_leaf), 1/d
   V3 op;              // origin rotated by kz (tri_test_fast)
   float sx, sy, sz;   // RayShearParams (src/Primitives.cpp:5-22)
   uint32_t permOfs;   // offset, in float4s, of the triangle-vertex copy rotated for this ray's kz
@@ -575,21 +575,43 @@ struct StreamQuery {
   int sp;             // entries below the top that live in `stack`
 };
 
-// Start of CompactBvh::intersect for the ray (o, d) with tMin = 0, tMax = inf: per-ray constants and the root test.
-// `stack` needs kMaxStack + 1 entries.
-RT_HD void stream_begin(const DevScene& sc, StreamQuery& q, V3 o, V3 d) {
-  q.o = o; q.d = d;
-  q.inv = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
+// Per-ray constants of a query, computed where the ray is made (the shading kernel for bounce rays, stream_begin for
+// camera rays): 1/d, RayShearParams, and `flags` = rotation of the triangle copies (bits 0-1: 0 for kz = 2, else
+// kz + 1) | kStreamFast (slab_fast / tri_test_fast apply: no NaN can occur in this query's box and triangle tests) |
+// kStreamRootHit (the ray passes the root's box test, tMin = 0, tMax = inf).
+constexpr uint32_t kStreamFast = 4u, kStreamRootHit = 8u;
+RT_HD void stream_prepare(const DevScene& sc, V3 o, V3 d, V3& inv, float& sx, float& sy, float& sz, uint32_t& flags) {
+  inv = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
   const Shear sh = make_shear(d);
-  q.sx = sh.sx; q.sy = sh.sy; q.sz = sh.sz;
-  q.op = permute(o, sh.kz);
-  q.permOfs = (sh.kz == 2 ? 0u : (uint32_t)sh.kz + 1u) * sc.numTris * 3u;
-  q.fast = sc.boundsFinite != 0u && sc.trisBounded != 0u && is_finite_f(q.inv.x) && is_finite_f(q.inv.y) && is_finite_f(q.inv.z) &&
-           below_bound(o.x) && below_bound(o.y) && below_bound(o.z) && below_bound(q.sx) && below_bound(q.sy) && below_bound(q.sz);
+  sx = sh.sx; sy = sh.sy; sz = sh.sz;
+  const bool fast = sc.boundsFinite != 0u && sc.trisBounded != 0u && is_finite_f(inv.x) && is_finite_f(inv.y) && is_finite_f(inv.z) &&
+                    below_bound(o.x) && below_bound(o.y) && below_bound(o.z) && below_bound(sx) && below_bound(sy) && below_bound(sz);
+  flags = (sh.kz == 2 ? 0u : (uint32_t)sh.kz + 1u) | (fast ? kStreamFast : 0u);
+  if (root_slab(sc, o, inv, 0.f, __builtin_huge_valf(), fast)) flags |= kStreamRootHit;
+}
+
+// Start of CompactBvh::intersect (tMin = 0, tMax = inf) for a ray whose constants are known. q.d is NOT set: only
+// sphere and disc tests read the direction, and the kernels fetch it there (see stream_leaf's `lazyD`).
+// `stack` needs kMaxStack + 1 entries.
+RT_HD void stream_begin_prepared(const DevScene& sc, StreamQuery& q, V3 o, V3 inv, float sx, float sy, float sz, uint32_t flags) {
+  q.o = o; q.inv = inv;
+  q.sx = sx; q.sy = sy; q.sz = sz;
+  const uint32_t perm = flags & 3u;
+  q.op = perm == 0u ? o : (perm == 1u ? mk(o.y, o.z, o.x) : mk(o.z, o.x, o.y));  // permute(o, kz)
+  q.permOfs = perm * sc.numTris * 3u;
+  q.fast = (flags & kStreamFast) != 0u;
   q.hitT = __builtin_huge_valf(); q.hitRef = kRefNone; q.b0 = q.b1 = q.b2 = 0.f;
   // bottom of the stack: popping it ends the query (its entry distance, -inf, is never beyond the closest hit)
   q.topRef = kRefNone; q.topE = -__builtin_huge_valf(); q.sp = 1;
-  q.ref = root_slab(sc, o, q.inv, 0.f, q.hitT, q.fast) ? sc.rootRef : kRefNone;
+  q.ref = (flags & kStreamRootHit) ? sc.rootRef : kRefNone;
+}
+RT_HD void stream_begin(const DevScene& sc, StreamQuery& q, V3 o, V3 d) {
+  V3 inv;
+  float sx, sy, sz;
+  uint32_t flags;
+  stream_prepare(sc, o, d, inv, sx, sy, sz, flags);
+  q.d = d;
+  stream_begin_prepared(sc, q, o, inv, sx, sy, sz, flags);
 }
 
 // Next deferred child. Returns true when that child's entry distance lies beyond the closest hit (the reference's
@@ -602,12 +624,13 @@ RT_HD bool stream_pop(StreamQuery& q, const uint2* stack) {
   return e > q.hitT;
 }
 
-// One inner-node step on the pair record `w` of q.ref. Returns stream_pop's "pop again".
+// One inner-node step on the pair record `w` of q.ref. kFast must equal q.fast (the kernels run their NaN-free
+// queries, all but a handful, through the <true> instantiation only). Returns stream_pop's "pop again".
+template <bool kFast>
 RT_HD bool stream_trav(StreamQuery& q, const PairWords& w, uint2* stack) {
   bool h0, h1;
   float e0, e1;
-  if (q.fast) pair_slabs<true>(w, q.o, q.inv, 0.f, q.hitT, h0, h1, e0, e1);
-  else pair_slabs<false>(w, q.o, q.inv, 0.f, q.hitT, h0, h1, e0, e1);
+  pair_slabs<kFast>(w, q.o, q.inv, 0.f, q.hitT, h0, h1, e0, e1);
   const bool goL = h0 && (!h1 || !(e1 < e0));  // ties go to the first child, like pre-order
   if (h0 && h1) {
     stack[q.sp++] = make_uint2(q.topRef, f_bits(q.topE));
@@ -623,12 +646,14 @@ RT_HD bool stream_trav(StreamQuery& q, const PairWords& w, uint2* stack) {
 
 // One leaf step on q.ref: primitive test (primLookup + Primitive::intersect, codelets/TraceCodelets.cpp:127-140) and
 // the acceptance of CompactBvh.hpp:124 (0 < t < closest; an equal t replaces the winner only if this primitive's leaf
-// precedes the winner's in the reference's pre-order walk). Returns stream_pop's "pop again".
-RT_HD bool stream_leaf(const DevScene& sc, StreamQuery& q, const uint2* stack) {
+// precedes the winner's in the reference's pre-order walk). lazyD: where the ray's direction {x, y, z, -} is kept when
+// q.d is not (nullptr = use q.d). Returns stream_pop's "pop again".
+template <bool kFast>
+RT_HD bool stream_leaf(const DevScene& sc, StreamQuery& q, const uint2* stack, const float4* lazyD = nullptr) {
   const uint32_t type = q.ref >> 30, index = q.ref & kLeafIndexMask;
   float t, b0 = 0.f, b1 = 0.f, b2 = 0.f;
   if (type == 0u) {
-    if (q.fast) {
+    if (kFast) {
       const float4* tv = sc.triVerts + (q.permOfs + 3u * index);
       const float4 a = RT_LDG(tv), b = RT_LDG(tv + 1), c = RT_LDG(tv + 2);
       t = tri_test_fast(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), q.op, q.sx, q.sy, q.sz, b0, b1, b2);
@@ -641,10 +666,11 @@ RT_HD bool stream_leaf(const DevScene& sc, StreamQuery& q, const uint2* stack) {
       t = tri_test(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), q.o, sh, b0, b1, b2);
     }
     t = t > 0.f ? t : __builtin_huge_valf();  // Mesh.hpp:90-93: only t > 0 replaces the inf default
-  } else if (type == 1u) {
-    t = sphere_test(RT_LDG(sc.spheres + index), q.o, q.d, 0.f);
   } else {
-    t = disc_test(sc.discs + 7u * index, q.o, q.d);
+    V3 d = q.d;
+    if (lazyD) { const float4 dd = RT_LDG(lazyD); d = mk(dd.x, dd.y, dd.z); }
+    if (type == 1u) t = sphere_test(RT_LDG(sc.spheres + index), q.o, d, 0.f);
+    else t = disc_test(sc.discs + 7u * index, q.o, d);
   }
   if (t > 0.f) {
     bool accept = t < q.hitT;
@@ -653,6 +679,23 @@ RT_HD bool stream_leaf(const DevScene& sc, StreamQuery& q, const uint2* stack) {
     if (accept) { q.hitT = t; q.hitRef = q.ref; q.b0 = b0; q.b1 = b1; q.b2 = b2; }
   }
   return stream_pop(q, stack);
+}
+
+// A whole query, one step after the other (host checks; the kernels' handful of queries that are not NaN-free).
+template <bool kFast, bool kCount>
+RT_HD void stream_run(const DevScene& sc, const uint4* __restrict__ pairs, StreamQuery& q, uint2* stack, const float4* lazyD,
+                      uint32_t& nodeVisits, uint32_t& primTests) {
+  while (q.ref != kRefNone) {
+    bool again;
+    if (ref_is_inner(q.ref)) {
+      if (kCount) nodeVisits += 2;
+      again = stream_trav<kFast>(q, fetch_pair<false>(pairs, ref_pair(q.ref)), stack);
+    } else {
+      if (kCount) primTests++;
+      again = stream_leaf<kFast>(sc, q, stack, lazyD);
+    }
+    while (again) again = stream_pop(q, stack);
+  }
 }
 
 // geomID / primID / global triangle index of a finished query's winner, as the reference reports them.

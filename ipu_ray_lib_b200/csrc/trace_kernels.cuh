@@ -484,7 +484,10 @@ __global__ void __launch_bounds__(768) path_trace_kernel(const TraceArgs a) {
           d = dielectric_dir(d, n, m.ior, u1, refracted);
           if (refracted) thr = thr * m.albedo;
         } else {
-          rgb = rgb * __int_as_float(0x7fc00000);  // result.rgb *= NaN (trace.cpp:167)
+          // result.rgb *= NaN (trace.cpp:167). With an environment light rgb is summed afterwards from the slots, so
+          // the poison has to travel in the path's colour (as in wf_shade_kernel)
+          if (kNif) color = color * __int_as_float(0x7fc00000);
+          else rgb = rgb * __int_as_float(0x7fc00000);
           flags |= kFlagError;
         }
       } else {

@@ -5,14 +5,15 @@
 // traversal loop. Here the per-path state lives in HBM between bounces and three kernels split the work:
 //
 //   (bounce 0)   no generate kernel: the first trace and shade kernels compute the camera ray of path p = (pixel, sample)
-//                themselves (per-(pixel,sample) RNG stream, jitter, first offsetRay) and treat the queue as the identity
-//   wf_trace     persistent warps; every lane pulls ray ids from the bounce's queue ON ITS OWN and pulls the next one
-//                the moment its traversal ends, so lanes never wait for a neighbour's long traversal; inside, each
-//                warp iteration runs one phase chosen by ballot (inner-node steps while enough lanes want one, else
-//                leaf tests, else the fetch of new rays)
-//   wf_shade     one thread per surviving path: updateHit, material, BxDF sample, roulette; writes the next ray (offset
-//                already applied) and compacts survivors into the other queue with a warp-aggregated append; finished
-//                paths write their colour / escape record (and the HitRecord if they are the last sample)
+//                themselves (per-(pixel,sample) RNG stream, jitter, first offsetRay); slot = path
+//   wf_trace     persistent warps; every lane takes the next live path's slot ON ITS OWN the moment its traversal ends,
+//                so lanes never wait for a neighbour's long traversal; inside, each warp iteration runs one phase
+//                chosen by ballot (inner-node steps while enough lanes want one, else leaf tests, else the fetch of
+//                new rays)
+//   wf_shade     one thread per live path: updateHit, material, BxDF sample, roulette; survivors are compacted: their
+//                records (next ray, offset applied, query constants prepared) are appended back to back to the other
+//                state array with a block-aggregated append; finished paths write their throughput / escape record
+//                (and the HitRecord if they are the last sample)
 //
 // The arithmetic per path is the megakernel's, statement for statement, so results are bit-identical; only the
 // grouping of work changes. rgb is accumulated afterwards in sample order by wf_accumulate_kernel.
@@ -21,21 +22,28 @@
 
 namespace rt {
 
-// Per-path record, kept as small as the arithmetic allows because wf_shade is bound by it (HBM): 64 B carried from
-// bounce to bounce + a 16 B hit (32 B when the scene interpolates normals). The running colour lives in slotColor (the
-// array the accumulate kernel reads anyway) and is only touched on emissive hits; the normal is carried only for paths
-// of the call's last sample, whose HitRecord is what the reference leaves in the ray stream.
+// Path state. It is indexed by SLOT, not by path: bounce b reads the records of its live paths back to back from
+// st[b & 1] (slot i = the i-th survivor of the previous bounce; at bounce 0 slot = path and nothing is read, the camera
+// path is computed) and writes the records of its own survivors back to back into st[(b & 1) ^ 1]. The two arrays ARE
+// the queues of the wavefront: every load and store of a record is a dense, fully coalesced 16-byte access, where a
+// record array indexed by path id is read through half-empty sectors from the second bounce on.
+// A record is 96 B (+ 16 B normal for paths of the call's last sample, whose HitRecord is what the reference leaves in
+// the ray stream) plus an 8 B hit (+ 16 B barycentrics when the scene interpolates normals). The running colour lives
+// in slotColor (the array the accumulate kernel reads anyway) and is only touched on emissive hits.
+struct WfState {
+  float4* rayO;  // origin.xyz (offset applied), w = bounce | flags << 8 | geomID << 16
+  float4* rayD;  // direction.xyz, w = primID bits
+  float4* rayI;  // 1 / direction: the shading kernel prepares the next query's constants (stream_prepare)
+  float4* rayS;  // RayShearParams sx, sy, sz, w = stream_prepare's flags
+  float4* thr;   // throughput.xyz, w = path id p = pixel * chunk + sample (bits)
+  uint4* rng;    // xoroshiro state {s0.lo, s0.hi, s1.lo, s1.hi}
+  float4* nrm;   // normal.xyz; read and written only for paths of the last sample
+};
 struct WfBuffers {
-  float4* rayO;       // [P] origin.xyz (offset applied), w = bounce | flags << 8 | geomID << 16
-  float4* rayD;       // [P] direction.xyz, w = primID bits
-  float4* thr;        // [P] throughput.xyz, w = tMax of the last intersect (HitRecord::r.tMax)
-  uint4* rng;         // [P] xoroshiro state {s0.lo, s0.hi, s1.lo, s1.hi}
-  float4* nrm;        // [P] normal.xyz; read and written only for paths of the last sample
-  float2* hitA;       // [P] closest t, leaf reference of the winner (kRefNone = no hit)
-  float4* hitB;       // [P] b0, b1, b2; only when the scene interpolates normals (else null)
-  uint32_t* queue[2];  // [P] path ids of the current / next bounce
-  const uint32_t* traceOrder;  // optional: the current queue's path ids in the order wf_trace should take them (null = queue order)
-  uint32_t* counts;   // [0],[1] queue sizes, [2] fetch cursor of wf_trace
+  WfState st[2];
+  float2* hitA;      // [slot] closest t, leaf reference of the winner (kRefNone = no hit)
+  float4* hitB;      // [slot] b0, b1, b2; only when the scene interpolates normals (else null)
+  uint32_t* counts;  // [0], [1]: live paths in st[0] / st[1]; [2]: fetch cursor of wf_trace
 };
 
 struct WfArgs {
@@ -44,7 +52,7 @@ struct WfArgs {
   uint32_t numPaths;  // numRays * chunk
   uint32_t chunk;
   uint32_t lastSample;  // the sample whose HitRecord is left in the ray stream (last of the whole call)
-  int qIn;            // queue index read by this launch
+  int qIn;            // state array read by this launch (bounce & 1)
   int travThreshold;
   unsigned long long* phaseStats;  // optional [bounce][3][2]: warp iterations and participating lanes per phase (count builds)
 };
@@ -64,7 +72,7 @@ __device__ __forceinline__ void wf_camera_path(const WfArgs& a, uint32_t p, V3& 
 }
 
 // ------------------------------------------------------------------------------------------------
-// wf_trace: one closest-hit query per path of the bounce's queue (CompactBvh::intersect, include/CompactBvh.hpp:80-139,
+// wf_trace: one closest-hit query per live path of the bounce (CompactBvh::intersect, include/CompactBvh.hpp:80-139,
 // near-first order over the pair table; the steps themselves are rt_prims.h "Streaming traversal").
 //
 // Persistent 1024-thread CTAs, the pair table staged in shared memory when it fits. Every lane owns one query at a
@@ -92,10 +100,12 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   asm volatile("" : "+r"(pairsShared));
   const DevScene& sc = a.t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
-  // bounce 0 (kFirst): the queue is the identity over all paths of the chunk and the rays are the camera rays
-  const uint32_t* queue = a.b.traceOrder ? a.b.traceOrder : a.b.queue[a.qIn];
+  // bounce 0 (kFirst): slot = path over all paths of the chunk and the rays are the camera rays
+  const WfState& in = a.b.st[a.qIn];
   const uint32_t count = kFirst ? a.numPaths : a.b.counts[a.qIn];
   uint32_t* cursor = a.b.counts + 2;
+  // the shading kernel that follows appends its survivors to the other array: empty it (nobody reads that counter here)
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[a.qIn ^ 1] = 0u;
   Counters cnt = {0u, 0u};
   unsigned nClosest = 0;
 
@@ -104,9 +114,9 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   q.sx = q.sy = q.sz = 0.f; q.permOfs = 0u; q.fast = true;
   q.hitT = __int_as_float(0x7f800000); q.hitRef = kRefNone; q.b0 = q.b1 = q.b2 = 0.f;
   q.ref = kRefNone; q.topRef = kRefNone; q.topE = 0.f; q.sp = 1;
-  uint32_t path = 0xFFFFFFFFu;  // the path whose query this is; none before the first fetch
+  uint32_t slot = 0xFFFFFFFFu;  // the slot whose query this is; none before the first fetch
   uint2 stack[kMaxStack + 1];   // deferred children below the register-held top: {reference, entry distance}
-  // ray ids are claimed from the bounce's queue kClaim at a time per warp: one same-address atomic per 128 rays
+  // slots are claimed kClaim at a time per warp: one same-address atomic per 128 rays
   constexpr uint32_t kClaim = 128;
   uint32_t wNext = 0, wEnd = 0;  // warp-uniform: the unclaimed part of this warp's current batch
   unsigned phaseIters[3] = {0u, 0u, 0u}, phaseLanes[3] = {0u, 0u, 0u};  // kCount builds: scheduler statistics
@@ -142,15 +152,15 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
           w = fetch_pair<false>(pairs, ref_pair(q.ref));
         }
         if (kCount) cnt.nodeVisits += 2;
-        again = stream_trav(q, w, stack);
+        again = stream_trav<true>(q, w, stack);
       }
     } else if (pick == WF_LEAF) {
       if (ref_is_leaf(q.ref)) {
         if (kCount) cnt.primTests++;
-        again = stream_leaf(sc, q, stack);
+        again = stream_leaf<true>(sc, q, stack, kFirst ? nullptr : in.rayD + slot);
       }
     } else {
-      // lanes that finished a query store its result and take the next ray ids of the warp's batch
+      // lanes that finished a query store its result and take the next slots of the warp's batch
       if (wNext == wEnd) {
         uint32_t claimBase = 0;
         if (lane == 0) claimBase = atomicAdd(cursor, kClaim);
@@ -163,34 +173,38 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
       const uint32_t qi = wNext + rank;
       wNext += min((uint32_t)cF, avail);
       if (served) {
-        if (path != 0xFFFFFFFFu) {
+        if (slot != 0xFFFFFFFFu) {
           // the shading kernel turns the winner's leaf reference into geomID / primID (stream_hit_ids)
-          a.b.hitA[path] = make_float2(q.hitT, __uint_as_float(q.hitRef));
-          if (a.b.hitB) a.b.hitB[path] = make_float4(q.b0, q.b1, q.b2, 0.f);
-          path = 0xFFFFFFFFu;
+          a.b.hitA[slot] = make_float2(q.hitT, __uint_as_float(q.hitRef));
+          if (a.b.hitB) a.b.hitB[slot] = make_float4(q.b0, q.b1, q.b2, 0.f);
+          slot = 0xFFFFFFFFu;
         }
         if (qi >= count) {
           q.ref = kRefDone;
         } else {
-          V3 o, d;
-          if (kFirst) {
-            path = qi;
-            Rng unused;
-            wf_camera_path(a, path, o, d, unused);
-          } else {
-            path = queue[qi];
-            const float4 ro = a.b.rayO[path], rd = a.b.rayD[path];
-            o = mk(ro.x, ro.y, ro.z);
-            d = mk(rd.x, rd.y, rd.z);
-          }
           // start of CompactBvh::intersect (tMin = 0, tMax = inf as set by the bounce loop, trace.cpp:128-130); a ray
           // that misses the root holds kRefNone again: its (empty) result is stored on the next fetch step
           nClosest++;
           if (kCount) cnt.nodeVisits++;
-          stream_begin(sc, q, o, d);
+          slot = qi;
+          if (kFirst) {
+            V3 o, d;
+            Rng unused;
+            wf_camera_path(a, slot, o, d, unused);
+            stream_begin(sc, q, o, d);
+          } else {
+            // bounce rays come with their constants (the shading kernel made them: stream_prepare)
+            const float4 ro = in.rayO[slot], ri = in.rayI[slot], rs = in.rayS[slot];
+            stream_begin_prepared(sc, q, mk(ro.x, ro.y, ro.z), mk(ri.x, ri.y, ri.z), rs.x, rs.y, rs.z, __float_as_uint(rs.w));
+          }
+          // the handful of queries in which a NaN could occur (a zero in the direction, coordinates beyond 2^20) take
+          // the NaN-preserving steps, the whole query here and now; the loop around only ever runs the fast steps
+          if (!q.fast) stream_run<false, kCount>(sc, sc.pairs, q, stack, kFirst ? nullptr : in.rayD + slot, cnt.nodeVisits, cnt.primTests);
         }
       }
     }
+    // one loop for both phases, after them: the reload of the stack top that a pop issues is then not consumed until the
+    // lane's next pop (inside the phases the compiler would move it into place at once and wait for it)
     while (again) again = stream_pop(q, stack);
   }
   if (kCount && a.phaseStats && lane == 0)
@@ -199,15 +213,22 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// wf_shade: the rest of one bounce-loop iteration (trace.cpp:133-184) for every live path, one thread per slot:
+// updateHit, material, BxDF sample, roulette. A surviving path's record (next ray with its offset applied and its query
+// constants prepared) is appended to the other state array; a finished path writes its throughput / escape record
+// (and the HitRecord if it belongs to the last sample). Appends are aggregated over the block: one same-address atomic
+// per 256 paths and array.
 template <bool kNif, bool kFirst>
 __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
   const TraceArgs& t = a.t;
   const DevScene& sc = t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
-  const uint32_t* queueIn = a.b.queue[a.qIn];
-  uint32_t* queueOut = a.b.queue[a.qIn ^ 1];
+  const WfState& in = a.b.st[a.qIn];
+  const WfState& out = a.b.st[a.qIn ^ 1];
   const uint32_t count = kFirst ? a.numPaths : a.b.counts[a.qIn];
   uint32_t* countOut = a.b.counts + (a.qIn ^ 1);
+  // the next trace kernel starts fetching at slot 0 again (this bounce's trace kernel is done with the cursor)
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[2] = 0u;
   unsigned nSamples = 0, nEscaped = 0;
   __shared__ uint32_t sCount[2][8];
   static_assert(256 / 32 == 8, "block-level append assumes 8 warps");
@@ -217,29 +238,28 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
   for (uint32_t r = 0; r < rounds; ++r) {
     const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < count;
-    bool survive = false;
+    bool survive = false, lastOne = false;
     uint32_t appendSlot = 0xFFFFFFFFu, p = 0;
+    // the survivor's next record, held in registers until its slot is known
+    V3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 0.f, -1.f), n = mk(0.f, 0.f, 1.f), thr = mk(1.f, 1.f, 1.f);
+    uint32_t bounce = 0, flags = 0, geomID = kInvalidGeom, primID = kInvalidPrim;
+    Rng rng;
+    rng.s0 = rng.s1 = 0ull;
     if (valid) {
-      p = kFirst ? i : queueIn[i];
-      const float2 ha = a.b.hitA[p];
+      const float2 ha = a.b.hitA[i];
       Hit hit;
       hit.t = ha.x;
       stream_hit_ids(sc, __float_as_uint(ha.y), hit.geomID, hit.primID, hit.tri);
       hit.node = 0; hit.b0 = hit.b1 = hit.b2 = 0.f;
-      if (a.b.hitB) { const float4 hb = a.b.hitB[p]; hit.b0 = hb.x; hit.b1 = hb.y; hit.b2 = hb.z; }
-      const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
-      const uint32_t s = t.firstSample + c;
-      const bool lastOne = s == a.lastSample;  // this path's HitRecord is the one left in the ray stream
-      V3 o, d, n = mk(0.f, 0.f, 1.f), thr = mk(1.f, 1.f, 1.f);
-      uint32_t bounce = 0, flags = 0, geomID = kInvalidGeom, primID = kInvalidPrim;
-      Rng rng;
+      if (a.b.hitB) { const float4 hb = a.b.hitB[i]; hit.b0 = hb.x; hit.b1 = hb.y; hit.b2 = hb.z; }
       if (kFirst) {
+        p = i;
         wf_camera_path(a, p, o, d, rng);  // same ray, same RNG state as the trace kernel started from
       } else {
-        const float4 ro = a.b.rayO[p], rd = a.b.rayD[p], th = a.b.thr[p];
-        const uint4 rs = a.b.rng[p];
+        const float4 ro = in.rayO[i], rd = in.rayD[i], th = in.thr[i];
+        const uint4 rs = in.rng[i];
+        p = __float_as_uint(th.w);
         o = mk(ro.x, ro.y, ro.z); d = mk(rd.x, rd.y, rd.z);
-        if (lastOne) { const float4 nn = a.b.nrm[p]; n = mk(nn.x, nn.y, nn.z); }
         thr = mk(th.x, th.y, th.z);
         const uint32_t packed = __float_as_uint(ro.w);
         bounce = packed & 0xffu; flags = (packed >> 8) & 0xffu; geomID = packed >> 16;
@@ -247,6 +267,10 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
         rng.s0 = (uint64_t)rs.x | ((uint64_t)rs.y << 32);
         rng.s1 = (uint64_t)rs.z | ((uint64_t)rs.w << 32);
       }
+      const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
+      const uint32_t s = t.firstSample + c;
+      lastOne = s == a.lastSample;  // this path's HitRecord is the one left in the ray stream
+      if (!kFirst && lastOne) { const float4 nn = in.nrm[i]; n = mk(nn.x, nn.y, nn.z); }
       V3 emitted = mk(0.f, 0.f, 0.f);  // thr * emission picked up at this bounce
       bool gotEmission = false, poisoned = false;
       if (bounce == 0) nSamples++;
@@ -302,12 +326,7 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
         sc3[0] = color.x; sc3[1] = color.y; sc3[2] = color.z;
       }
       if (!ended) {
-        const V3 on = offset_origin(o, d, n);  // offsetRay at the top of the next iteration (trace.cpp:126)
-        a.b.rayO[p] = make_float4(on.x, on.y, on.z, __uint_as_float(bounce | (flags << 8) | (geomID << 16)));
-        a.b.rayD[p] = make_float4(d.x, d.y, d.z, __uint_as_float(primID));
-        a.b.thr[p] = make_float4(thr.x, thr.y, thr.z, tMaxOut);
-        a.b.rng[p] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
-        if (lastOne) a.b.nrm[p] = make_float4(n.x, n.y, n.z, 0.f);
+        o = offset_origin(o, d, n);  // offsetRay at the top of the next iteration (trace.cpp:126)
         survive = true;
       } else {
         if (escaped) nEscaped++;
@@ -332,9 +351,8 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
         }
       }
     }
-    // regroup: survivors go to the other queue, escaped slots to the NIF queue. Appends are aggregated over the whole
-    // block (one same-address atomic per 256 paths and queue): every warp posts its two counts, warp 0 reserves both
-    // ranges, each warp then knows its offset.
+    // regroup: survivors go to the other state array, escaped slots to the NIF queue. Every warp posts its two counts,
+    // warp 0 reserves both ranges, each warp then knows its offset.
     {
       const unsigned mS = __ballot_sync(full, survive);
       const unsigned mE = kNif ? __ballot_sync(full, appendSlot != 0xFFFFFFFFu) : 0u;
@@ -357,7 +375,22 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
         if (lane < 16) sCount[q][w] = base + incl - v;
       }
       __syncthreads();
-      if (survive) queueOut[sCount[0][warp] + __popc(mS & ((1u << lane) - 1u))] = p;
+      if (survive) {
+        // consecutive survivors of a warp write consecutive records: full sectors
+        const uint32_t j = sCount[0][warp] + __popc(mS & ((1u << lane) - 1u));
+        out.rayO[j] = make_float4(o.x, o.y, o.z, __uint_as_float(bounce | (flags << 8) | (geomID << 16)));
+        out.rayD[j] = make_float4(d.x, d.y, d.z, __uint_as_float(primID));
+        out.thr[j] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(p));
+        out.rng[j] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
+        if (lastOne) out.nrm[j] = make_float4(n.x, n.y, n.z, 0.f);
+        // constants of the next query, computed here where every lane has a ray (wf_trace's fetch phase runs at ~20 lanes)
+        V3 inv;
+        float sx, sy, sz;
+        uint32_t qflags;
+        stream_prepare(sc, o, d, inv, sx, sy, sz, qflags);
+        out.rayI[j] = make_float4(inv.x, inv.y, inv.z, 0.f);
+        out.rayS[j] = make_float4(sx, sy, sz, __uint_as_float(qflags));
+      }
       if (kNif && appendSlot != 0xFFFFFFFFu) t.escapeQueue[sCount[1][warp] + __popc(mE & ((1u << lane) - 1u))] = appendSlot;
       __syncthreads();  // sCount is rewritten in the next round
     }
@@ -419,27 +452,5 @@ __global__ void __launch_bounds__(256) wf_accumulate_kernel(float* rays, uint32_
   if (threadIdx.x < pixels) { tr[TR_RGB] = rgb.x; tr[TR_RGB + 1] = rgb.y; tr[TR_RGB + 2] = rgb.z; }
 }
 
-#ifdef B200RT_EXPERIMENT_SORT
-// EXPERIMENT (make experiments): sort key of every queued path = (origin cell 5 bits per axis | octahedral direction
-// bin 3 + 3 bits), to measure how much ray coherence is worth to wf_trace. Entries past the queue's end get the
-// largest key.
-__global__ void wf_sort_key_kernel(const WfArgs a, uint32_t* keys, uint32_t* ids, float3 boxMin, float3 boxInvExt) {
-  const uint32_t count = a.b.counts[a.qIn];
-  const uint32_t* queue = a.b.queue[a.qIn];
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.numPaths; i += gridDim.x * blockDim.x) {
-    if (i >= count) { keys[i] = 0xFFFFFFFFu; ids[i] = 0u; continue; }
-    const uint32_t p = queue[i];
-    const float4 ro = a.b.rayO[p], rd = a.b.rayD[p];
-    auto cell = [](float x, float mn, float inv) { const int c = (int)((x - mn) * inv * 32.f); return (uint32_t)min(max(c, 0), 31); };
-    const uint32_t cx = cell(ro.x, boxMin.x, boxInvExt.x), cy = cell(ro.y, boxMin.y, boxInvExt.y), cz = cell(ro.z, boxMin.z, boxInvExt.z);
-    const float n1 = fabsf(rd.x) + fabsf(rd.y) + fabsf(rd.z);
-    float u = rd.x / n1, v = rd.y / n1;
-    if (rd.z < 0.f) { const float uu = (1.f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f), vv = (1.f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f); u = uu; v = vv; }
-    const uint32_t du = (uint32_t)min(max((int)((u * .5f + .5f) * 8.f), 0), 7), dv = (uint32_t)min(max((int)((v * .5f + .5f) * 8.f), 0), 7);
-    keys[i] = (((cz << 10) | (cy << 5) | cx) << 6) | (dv << 3) | du;
-    ids[i] = p;
-  }
-}
-#endif
 
 }  // namespace rt

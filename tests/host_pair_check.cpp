@@ -89,21 +89,20 @@ int hostpair_stream_intersect(const b200rt_scene_desc* d, const void* raysIn, si
   for (size_t i = 0; i < n; ++i) {
     const float* r = rays + 8 * i;
     const rt::V3 o = rt::mk(r[0], r[1], r[2]), dir = rt::mk(r[4], r[5], r[6]);
+    // as the kernels do it: constants prepared where the ray is made, the direction kept aside (lazyD)
     rt::StreamQuery q;
-    rt::stream_begin(v.dev, q, o, dir);
-    nv += 1;
+    rt::V3 inv;
+    float sx, sy, sz;
+    uint32_t flags;
+    rt::stream_prepare(v.dev, o, dir, inv, sx, sy, sz, flags);
+    rt::stream_begin_prepared(v.dev, q, o, inv, sx, sy, sz, flags);
+    q.d = rt::mk(0.f, 0.f, 0.f);
+    const float4 lazy = make_float4(dir.x, dir.y, dir.z, 0.f);
     nf += q.fast ? 1 : 0;
-    while (q.ref != rt::kRefNone) {
-      bool again;
-      if (rt::ref_is_inner(q.ref)) {
-        nv += 2;
-        again = rt::stream_trav(q, rt::fetch_pair<false>(v.dev.pairs, rt::ref_pair(q.ref)), stack.data());
-      } else {
-        np += 1;
-        again = rt::stream_leaf(v.dev, q, stack.data());
-      }
-      while (again) again = rt::stream_pop(q, stack.data());
-    }
+    uint32_t a = 1, b = 0;
+    if (q.fast) rt::stream_run<true, true>(v.dev, v.dev.pairs, q, stack.data(), &lazy, a, b);
+    else rt::stream_run<false, true>(v.dev, v.dev.pairs, q, stack.data(), &lazy, a, b);
+    nv += a; np += b;
     b200rt_hit h;
     uint32_t tri;
     h.t = q.hitT;
