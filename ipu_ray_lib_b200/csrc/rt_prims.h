@@ -631,14 +631,21 @@ RT_HD bool stream_trav(StreamQuery& q, const PairWords& w, uint2* stack) {
   bool h0, h1;
   float e0, e1;
   pair_slabs<kFast>(w, q.o, q.inv, 0.f, q.hitT, h0, h1, e0, e1);
-  const bool goL = h0 && (!h1 || !(e1 < e0));  // ties go to the first child, like pre-order
+  // the second child is entered first only if it is hit and the first child is not, or is hit farther away
+  // (ties go to the first child, like pre-order). Near / far are selected BEFORE the branches on purpose: with the
+  // selects written inside `if (h0 && h1)` nvcc 12.9 folded them to "first child near" in the <true> instantiation
+  // (found on the GPU as lost subtrees; tests/test_gpu_parity.py pins it).
+  const bool rightFirst = h1 && (!h0 || e1 < e0);
+  const uint32_t nearRef = rightFirst ? w.q2.y : w.q0.w;
+  const uint32_t farRef = rightFirst ? w.q0.w : w.q2.y;
+  const float farE = rightFirst ? e0 : e1;
   if (h0 && h1) {
     stack[q.sp++] = make_uint2(q.topRef, f_bits(q.topE));
-    q.topRef = goL ? w.q2.y : w.q0.w;
-    q.topE = goL ? e1 : e0;
+    q.topRef = farRef;
+    q.topE = farE;
   }
   if (h0 || h1) {
-    q.ref = goL ? w.q0.w : w.q2.y;
+    q.ref = nearRef;
     return false;
   }
   return stream_pop(q, stack);
