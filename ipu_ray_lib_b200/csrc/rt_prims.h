@@ -635,7 +635,10 @@ RT_HD bool stream_trav(StreamQuery& q, const PairWords& w, uint2* stack) {
   // (ties go to the first child, like pre-order). Near / far are selected BEFORE the branches on purpose: with the
   // selects written inside `if (h0 && h1)` nvcc 12.9 folded them to "first child near" in the <true> instantiation
   // (found on the GPU as lost subtrees; tests/test_gpu_parity.py pins it).
-  const bool rightFirst = h1 && (!h0 || e1 < e0);
+  // = h1 && (!h0 || e1 < e0), written as ONE unordered compare: a missed first child counts as NaN-far away (entry
+  // distances themselves are never NaN: they start at tMin and are only replaced by values that compare greater)
+  const float e0x = h0 ? e0 : bits_f(0x7fc00000u);
+  const bool rightFirst = h1 && !(e0x <= e1);
   const uint32_t nearRef = rightFirst ? w.q2.y : w.q0.w;
   const uint32_t farRef = rightFirst ? w.q0.w : w.q2.y;
   const float farE = rightFirst ? e0 : e1;
