@@ -396,8 +396,6 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
         w.b.hitA = (float2*)sc.wfHitA.p; w.b.hitB = needBary ? (float4*)sc.wfHitB.p : nullptr;
         w.b.counts = (uint32_t*)sc.wfCounts.p;
         w.lastSample = first + count - 1;
-        static const int envWf = [] { const char* e = std::getenv("B200RT_WF_THRESHOLD"); return e ? std::atoi(e) : 8; }();
-        w.travThreshold = std::max(envWf, 1);
       }
       for (uint32_t s0 = first; s0 < first + count; s0 += chunk) {
         const uint32_t c = std::min(chunk, first + count - s0);

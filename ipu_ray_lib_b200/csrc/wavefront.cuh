@@ -53,7 +53,6 @@ struct WfArgs {
   uint32_t chunk;
   uint32_t lastSample;  // the sample whose HitRecord is left in the ray stream (last of the whole call)
   int qIn;            // state array read by this launch (bounce & 1)
-  int travThreshold;
   unsigned long long* phaseStats;  // optional [bounce][3][2]: warp iterations and participating lanes per phase (count builds)
 };
 
@@ -79,10 +78,12 @@ __device__ __forceinline__ void wf_camera_path(const WfArgs& a, uint32_t p, V3& 
 // time and is in one of three phases, told apart by the node reference it holds: TRAV (an inner node: load its 48-byte
 // pair record, test both child boxes, descend / defer / pop), LEAF (a leaf: run the primitive test, then pop) or FETCH
 // (query finished: store the hit, take the next ray of the warp's batch, test the root). A warp iteration executes ONE
-// phase, chosen by ballot: inner-node steps as long as at least `travThreshold` lanes want one (a single ballot on
+// phase, chosen by ballot: inner-node steps as long as at least kTravThreshold lanes want one (a single ballot on
 // that path), otherwise whichever phase most lanes wait for. Lanes therefore never wait for a neighbour's long
 // traversal, only for their phase to be scheduled.
 enum : uint32_t { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2 };
+// measured flat between 8 and 16 on the B200 and in the scheduler model (scripts/wf_sched_sim.cpp)
+constexpr int kTravThreshold = 8;
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
     uint32_t pick = WF_TRAV;
     unsigned mF = 0u;
     int cF = 0, cL = 0;
-    if (cT < a.travThreshold) {
+    if (cT < kTravThreshold) {
       const unsigned mL = __ballot_sync(full, ref_is_leaf(q.ref));
       mF = __ballot_sync(full, q.ref == kRefNone);
       if (!(mT | mL | mF)) break;  // every lane is kRefDone
@@ -230,12 +231,13 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
   // the next trace kernel starts fetching at slot 0 again (this bounce's trace kernel is done with the cursor)
   if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[2] = 0u;
   unsigned nSamples = 0, nEscaped = 0;
-  __shared__ uint32_t sCount[2][8];
+  __shared__ uint32_t sCountBuf[2][2][8];  // [round parity][queue][warp]: the next round posts into the other half
   static_assert(256 / 32 == 8, "block-level append assumes 8 warps");
   // whole blocks iterate together (uniform trip count) so the ballots and barriers below see converged threads
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t rounds = (count + stride - 1) / stride;
   for (uint32_t r = 0; r < rounds; ++r) {
+    uint32_t (*sCount)[8] = sCountBuf[r & 1u];
     const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < count;
     bool survive = false, lastOne = false;
@@ -392,7 +394,8 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
         out.rayS[j] = make_float4(sx, sy, sz, __uint_as_float(qflags));
       }
       if (kNif && appendSlot != 0xFFFFFFFFu) t.escapeQueue[sCount[1][warp] + __popc(mE & ((1u << lane) - 1u))] = appendSlot;
-      __syncthreads();  // sCount is rewritten in the next round
+      // no third barrier: the next round posts its counts into the other half of sCountBuf, and a warp can only get
+      // two rounds ahead of another by passing that round's first barrier, which every warp must reach
     }
   }
   flush_counters(t.counters, 0u, 0u, Counters{0u, 0u}, nSamples, nEscaped);
