@@ -413,7 +413,7 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
           w.t = a;
           w.chunk = c;
           w.numPaths = (uint32_t)((size_t)c * n);
-          const int gridSmall = sc.numSMs * 8;
+          const int gridSmall = sc.numSMs * rt::kShadeBlocksPerSM;
           static const int envWfThreads = [] { const char* e = std::getenv("B200RT_WF_THREADS"); return e ? std::atoi(e) : 0; }();
           // wf_trace needs <= 64 registers: 32 warps per SM (measured 5 % faster than 24)
           const int wfBlock = envWfThreads > 0 ? std::min(envWfThreads, 1024) : (L.shared ? 1024 : L.block);

@@ -219,8 +219,11 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
 // constants prepared) is appended to the other state array; a finished path writes its throughput / escape record
 // (and the HitRecord if it belongs to the last sample). Appends are aggregated over the block: one same-address atomic
 // per 256 paths and array.
+// 6 blocks per SM (40 registers): the kernel waits on dependent loads (hit -> leafInfo -> vertices -> material), so it is
+// occupancy that buys time here; measured 1.6 ms per launch at 1 block's worth of registers, 1.0 at 4-8.
+constexpr int kShadeBlocksPerSM = 6;
 template <bool kNif, bool kFirst>
-__global__ void __launch_bounds__(256) wf_shade_kernel(const WfArgs a) {
+__global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const WfArgs a) {
   const TraceArgs& t = a.t;
   const DevScene& sc = t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
