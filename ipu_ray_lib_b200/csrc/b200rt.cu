@@ -81,7 +81,7 @@ struct b200rt_scene {
   b200rt_scene_desc desc{};  // scalars only are used after creation
   rt::DevScene dev{};
   uint32_t nodeBytes = 0, pairBytes = 0;
-  DeviceBuffer nodes, pairs, leafOrig, leafInfo, geoms, triVerts, triNormals, spheres, discs, matIDs, materials;
+  DeviceBuffer nodes, pairs, leafOrig, leafInfo, geoms, triVerts, triNormals, triFaceNormals, spheres, discs, matIDs, materials;
   DeviceBuffer workCounter, counters, primA, primB;
   DeviceBuffer rays;                                   // device copy of the stream (host-buffer entry point)
   DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
@@ -95,7 +95,7 @@ struct b200rt_scene {
   ~b200rt_scene() {
     cudaSetDevice(device);
     if (nif) rt::nif_destroy(nif);
-    for (DeviceBuffer* b : {&nodes, &pairs, &leafOrig, &leafInfo, &geoms, &triVerts, &triNormals, &spheres, &discs, &matIDs, &materials,
+    for (DeviceBuffer* b : {&nodes, &pairs, &leafOrig, &leafInfo, &geoms, &triVerts, &triNormals, &triFaceNormals, &spheres, &discs, &matIDs, &materials,
                             &workCounter, &counters, &primA, &primB, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
                             &escapeCount, &wfHitA, &wfHitB, &wfCounts})
       b->release();
@@ -412,6 +412,7 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
         } else {
           w.t = a;
           w.chunk = c;
+          w.chunkShift = (c & (c - 1)) == 0 ? __builtin_ctz(c) : -1;
           w.numPaths = (uint32_t)((size_t)c * n);
           const int gridSmall = sc.numSMs * rt::kShadeBlocksPerSM;
           static const int envWfThreads = [] { const char* e = std::getenv("B200RT_WF_THREADS"); return e ? std::atoi(e) : 0; }();
@@ -613,6 +614,7 @@ int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
   CU_TRY(sc->geoms.upload(tables.geoms.data(), tables.geoms.size() * sizeof(rt::GeomEntry)));
   CU_TRY(sc->triVerts.upload(tables.triVerts.data(), tables.triVerts.size() * sizeof(float)));
   if (d->num_normals) CU_TRY(sc->triNormals.upload(tables.triNormals.data(), tables.triNormals.size() * sizeof(float)));
+  CU_TRY(sc->triFaceNormals.upload(tables.triFaceNormals.data(), tables.triFaceNormals.size() * sizeof(float)));
   CU_TRY(sc->spheres.upload(d->spheres, (size_t)d->num_spheres * 16));
   CU_TRY(sc->discs.upload(d->discs, (size_t)d->num_discs * 28));
   CU_TRY(sc->matIDs.upload(d->mat_ids, (size_t)d->num_mat_ids * 4));
@@ -624,6 +626,7 @@ int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
   sc->dev.geoms = (const rt::GeomEntry*)sc->geoms.p;
   sc->dev.triVerts = (const float4*)sc->triVerts.p;
   sc->dev.triNormals = d->num_normals ? (const float4*)sc->triNormals.p : nullptr;
+  sc->dev.triFaceNormals = d->num_tris ? (const float4*)sc->triFaceNormals.p : nullptr;
   sc->dev.spheres = (const float4*)sc->spheres.p;
   sc->dev.discs = (const float*)sc->discs.p;
   sc->dev.matIDs = (const uint32_t*)sc->matIDs.p;

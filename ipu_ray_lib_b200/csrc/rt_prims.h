@@ -44,6 +44,8 @@ struct DevScene {
   const float4* triVerts;    // [3][num_tris][3]  p0,p1,p2 gathered from Triangle[] + Vec3fa[] (w unused); copy 0 as
                              // given, copies 1 and 2 with the components rotated for kz = 0 / kz = 1 (see tri_test_fast)
   const float4* triNormals;  // [num_tris][3]  vertex normals, or nullptr when the scene has none
+  const float4* triFaceNormals;  // [num_tris] normalized(cross(p1 - p0, p2 - p0)), computed once at scene creation (host and
+                             // device arithmetic agree bit for bit, see rt_math.h); nullptr = compute from the vertices
   const float4* spheres;     // {x,y,z,radius}
   const float* discs;        // {nx,ny,nz,r,cx,cy,cz}
   const uint32_t* matIDs;    // [num_geometry]
@@ -348,6 +350,7 @@ RT_HD V3 prim_normal(const DevScene& sc, uint32_t geomID, uint32_t tri, float b0
   g.type = gw.x; g.first = gw.y;
   if (g.type == 0u) {
     if (sc.triNormals == nullptr) {
+      if (sc.triFaceNormals != nullptr) { const float4 fn = RT_LDG(sc.triFaceNormals + tri); return mk(fn.x, fn.y, fn.z); }
       const float4* tv = sc.triVerts + 3u * tri;
       const float4 a = RT_LDG(tv), b = RT_LDG(tv + 1), c = RT_LDG(tv + 2);
       const V3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
@@ -502,8 +505,8 @@ RT_HD bool pair_any_hit(const DevScene& sc, const uint4* __restrict__ pairs, V3 
 // What keeps the steps short:
 //  * the node a lane holds is ONE word, the child reference itself (inner: kRefInner | pair, leaf: type << 30 | index,
 //    kRefNone: query finished), so descending is a select and the phase of a lane is a comparison;
-//  * deferred children are stacked as {reference, entry distance}; the top of the stack lives in two registers, so a
-//    pop is two moves plus a reload that nothing waits for;
+//  * deferred children are stacked as {reference, entry distance}; the two top entries live in registers, so a pop is
+//    a few moves plus a reload from local memory that is only consumed two pops later;
 //  * geomID / primID of the winner are looked up once per query from leafInfo (by the shading kernel), equal-t ties
 //    compare the reference node indices stored there;
 //  * triangles of a NaN-free query (fast_query_ok) are tested by tri_test_fast on vertex copies whose components are
@@ -570,8 +573,10 @@ struct StreamQuery {
   uint32_t hitRef;    // leaf reference of the winner, kRefNone = nothing hit
   float b0, b1, b2;   // barycentrics of the winning triangle
   uint32_t ref;       // node held: inner (ref_is_inner), leaf (ref_is_leaf) or kRefNone = query finished
-  uint32_t topRef;    // top of the stack of deferred children, kept in registers
+  uint32_t topRef;    // the two top entries of the stack of deferred children live in registers
   float topE;
+  uint32_t top2Ref;   // ... and the entry below it: a pop's reload from memory is then only consumed two pops later
+  float top2E;
   int sp;             // entries below the top that live in `stack`
 };
 
@@ -603,6 +608,7 @@ RT_HD void stream_begin_prepared(const DevScene& sc, StreamQuery& q, V3 o, V3 in
   q.hitT = __builtin_huge_valf(); q.hitRef = kRefNone; q.b0 = q.b1 = q.b2 = 0.f;
   // bottom of the stack: popping it ends the query (its entry distance, -inf, is never beyond the closest hit)
   q.topRef = kRefNone; q.topE = -__builtin_huge_valf(); q.sp = 1;
+  q.top2Ref = kRefNone; q.top2E = -__builtin_huge_valf();
   q.ref = (flags & kStreamRootHit) ? sc.rootRef : kRefNone;
 }
 RT_HD void stream_begin(const DevScene& sc, StreamQuery& q, V3 o, V3 d) {
@@ -620,7 +626,8 @@ RT_HD bool stream_pop(StreamQuery& q, const uint2* stack) {
   const float e = q.topE;
   q.ref = q.topRef;
   const uint2 below = stack[--q.sp];
-  q.topRef = below.x; q.topE = bits_f(below.y);
+  q.topRef = q.top2Ref; q.topE = q.top2E;
+  q.top2Ref = below.x; q.top2E = bits_f(below.y);
   return e > q.hitT;
 }
 
@@ -643,7 +650,8 @@ RT_HD bool stream_trav(StreamQuery& q, const PairWords& w, uint2* stack) {
   const uint32_t farRef = rightFirst ? w.q0.w : w.q2.y;
   const float farE = rightFirst ? e0 : e1;
   if (h0 && h1) {
-    stack[q.sp++] = make_uint2(q.topRef, f_bits(q.topE));
+    stack[q.sp++] = make_uint2(q.top2Ref, f_bits(q.top2E));
+    q.top2Ref = q.topRef; q.top2E = q.topE;
     q.topRef = farRef;
     q.topE = farE;
   }

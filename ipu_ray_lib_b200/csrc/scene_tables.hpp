@@ -16,6 +16,7 @@ struct SceneTables {
   std::vector<GeomEntry> geoms;
   std::vector<float> triVerts;    // [3][num_tris][3][4]: as given, then rotated for kz = 0 (y,z,x) and kz = 1 (z,x,y)
   bool trisBounded = true;        // every vertex finite and below 2^20 in magnitude (tri_test_fast)
+  std::vector<float> triFaceNormals;  // [num_tris][4]: Primitive::normal of a mesh triangle without vertex normals (Mesh.hpp:106-121)
   std::vector<float> triNormals;  // same shape, empty when the scene has no normals
   PairTable pairs;
 };
@@ -72,6 +73,14 @@ inline std::string build_scene_tables(const b200rt_scene_desc& d, SceneTables& o
         if (d.num_normals) std::memcpy(&out.triNormals[12 * gt + 4 * k], normals + 3 * gv, 12);
       }
     }
+  }
+  out.triFaceNormals.assign((size_t)d.num_tris * 4, 0.f);
+  for (uint32_t t = 0; t < d.num_tris; ++t) {
+    const float* v = &out.triVerts[12 * (size_t)t];
+    const V3 p0 = mk(v[0], v[1], v[2]), p1 = mk(v[4], v[5], v[6]), p2 = mk(v[8], v[9], v[10]);
+    const V3 n = normalized(cross(p1 - p0, p2 - p0));  // same statement as prim_normal
+    float* o = &out.triFaceNormals[4 * (size_t)t];
+    o[0] = n.x; o[1] = n.y; o[2] = n.z;
   }
   return build_pair_table(d.bvh_nodes, d.num_bvh_nodes, out.geoms.data(), d.num_geometry, primCount.data(), d.num_tris,
                           d.num_spheres, d.num_discs, out.pairs);

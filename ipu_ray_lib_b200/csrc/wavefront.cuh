@@ -51,6 +51,7 @@ struct WfArgs {
   WfBuffers b;
   uint32_t numPaths;  // numRays * chunk
   uint32_t chunk;
+  int chunkShift;     // log2(chunk) when chunk is a power of two (the default chunks are), else -1
   uint32_t lastSample;  // the sample whose HitRecord is left in the ray stream (last of the whole call)
   int qIn;            // state array read by this launch (bounce & 1)
   unsigned long long* phaseStats;  // optional [bounce][3][2]: warp iterations and participating lanes per phase (count builds)
@@ -62,7 +63,7 @@ struct WfArgs {
 // shade kernel both call this (a few hundred instructions) instead of writing and re-reading 80 B per path.
 __device__ __forceinline__ void wf_camera_path(const WfArgs& a, uint32_t p, V3& o, V3& d, Rng& rng) {
   const TraceArgs& t = a.t;
-  const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
+  const uint32_t idx = a.chunkShift >= 0 ? p >> a.chunkShift : p / a.chunk, c = p - idx * a.chunk;
   const float* tr = t.rays + (size_t)idx * TR_WORDS;
   const float row = tr[TR_ROW], col = tr[TR_COL];
   const uint32_t pixelIndex = (uint32_t)row * (uint32_t)t.imageWidth + (uint32_t)col;
@@ -82,8 +83,9 @@ __device__ __forceinline__ void wf_camera_path(const WfArgs& a, uint32_t p, V3& 
 // that path), otherwise whichever phase most lanes wait for. Lanes therefore never wait for a neighbour's long
 // traversal, only for their phase to be scheduled.
 enum : uint32_t { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2 };
-// measured flat between 8 and 16 on the B200 and in the scheduler model (scripts/wf_sched_sim.cpp)
-constexpr int kTravThreshold = 8;
+// measured on the B200 (scripts/wf_kernel_times.py, 1.940 / 1.888 / 1.938 ms per launch at 8 / 12 / 16); the scheduler
+// model (scripts/wf_sched_sim.cpp) has its optimum at the same place
+constexpr int kTravThreshold = 12;
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   q.o = q.op = q.inv = mk(0.f, 0.f, 0.f); q.d = mk(0.f, 0.f, -1.f);
   q.sx = q.sy = q.sz = 0.f; q.permOfs = 0u; q.fast = true;
   q.hitT = __int_as_float(0x7f800000); q.hitRef = kRefNone; q.b0 = q.b1 = q.b2 = 0.f;
-  q.ref = kRefNone; q.topRef = kRefNone; q.topE = 0.f; q.sp = 1;
+  q.ref = kRefNone; q.topRef = q.top2Ref = kRefNone; q.topE = q.top2E = 0.f; q.sp = 1;
   uint32_t slot = 0xFFFFFFFFu;  // the slot whose query this is; none before the first fetch
   uint2 stack[kMaxStack + 1];   // deferred children below the register-held top: {reference, entry distance}
   // slots are claimed kClaim at a time per warp: one same-address atomic per 128 rays
@@ -123,9 +125,9 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   unsigned phaseIters[3] = {0u, 0u, 0u}, phaseLanes[3] = {0u, 0u, 0u};  // kCount builds: scheduler statistics
 
   while (true) {
-    const bool wantT = ref_is_inner(q.ref);
-    const unsigned mT = __ballot_sync(full, wantT);
-    const int cT = __popc(mT);
+    bool wantT = ref_is_inner(q.ref);
+    unsigned mT = __ballot_sync(full, wantT);
+    int cT = __popc(mT);
     uint32_t pick = WF_TRAV;
     unsigned mF = 0u;
     int cF = 0, cL = 0;
@@ -136,25 +138,35 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
       cL = __popc(mL); cF = __popc(mF);
       if (!(cT >= cL && cT >= cF)) pick = cL >= cF ? WF_LEAF : WF_FETCH;
     }
-    if (kCount && a.phaseStats && lane == 0) {
+    if (kCount && a.phaseStats && lane == 0 && pick != WF_TRAV) {
       phaseIters[pick] += 1u;
-      phaseLanes[pick] += (unsigned)(pick == WF_TRAV ? cT : (pick == WF_LEAF ? cL : cF));
+      phaseLanes[pick] += (unsigned)(pick == WF_LEAF ? cL : cF);
     }
 
     bool again = false;  // the node just popped is culled: keep popping
     if (pick == WF_TRAV) {
-      if (wantT) {
-        PairWords w;
-        if (kShared) {
-          // (kRefInner | pair) * 48 wraps to pair * 48 in 32 bits: the reference needs no mask
-          const uint32_t at = pairsShared + q.ref * 48u;
-          w.q0 = lds128(at); w.q1 = lds128(at + 16u); w.q2 = lds128(at + 32u);
-        } else {
-          w = fetch_pair<false>(pairs, ref_pair(q.ref));
+      // inner-node steps, one after the other while enough lanes want one: the loop votes for itself, so a run of steps
+      // pays for one ballot each instead of a trip through the phase selection above
+      do {
+        if (kCount && a.phaseStats && lane == 0) { phaseIters[WF_TRAV] += 1u; phaseLanes[WF_TRAV] += (unsigned)cT; }
+        again = false;
+        if (wantT) {
+          PairWords w;
+          if (kShared) {
+            // (kRefInner | pair) * 48 wraps to pair * 48 in 32 bits: the reference needs no mask
+            const uint32_t at = pairsShared + q.ref * 48u;
+            w.q0 = lds128(at); w.q1 = lds128(at + 16u); w.q2 = lds128(at + 32u);
+          } else {
+            w = fetch_pair<false>(pairs, ref_pair(q.ref));
+          }
+          if (kCount) cnt.nodeVisits += 2;
+          again = stream_trav<true>(q, w, stack);
         }
-        if (kCount) cnt.nodeVisits += 2;
-        again = stream_trav<true>(q, w, stack);
-      }
+        while (again) again = stream_pop(q, stack);
+        wantT = ref_is_inner(q.ref);
+        mT = __ballot_sync(full, wantT);
+        cT = __popc(mT);
+      } while (cT >= kTravThreshold);
     } else if (pick == WF_LEAF) {
       if (ref_is_leaf(q.ref)) {
         if (kCount) cnt.primTests++;
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const 
         rng.s0 = (uint64_t)rs.x | ((uint64_t)rs.y << 32);
         rng.s1 = (uint64_t)rs.z | ((uint64_t)rs.w << 32);
       }
-      const uint32_t idx = p / a.chunk, c = p - idx * a.chunk;
+      const uint32_t idx = a.chunkShift >= 0 ? p >> a.chunkShift : p / a.chunk, c = p - idx * a.chunk;
       const uint32_t s = t.firstSample + c;
       lastOne = s == a.lastSample;  // this path's HitRecord is the one left in the ray stream
       if (!kFirst && lastOne) { const float4 nn = in.nrm[i]; n = mk(nn.x, nn.y, nn.z); }

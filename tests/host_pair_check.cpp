@@ -24,6 +24,7 @@ bool make_view(const b200rt_scene_desc* d, HostView& v) {
   s.geoms = v.tables.geoms.data();
   s.triVerts = (const float4*)v.tables.triVerts.data();
   s.triNormals = v.tables.triNormals.empty() ? nullptr : (const float4*)v.tables.triNormals.data();
+  s.triFaceNormals = (const float4*)v.tables.triFaceNormals.data();
   s.spheres = (const float4*)d->spheres;
   s.discs = d->discs;
   s.matIDs = d->mat_ids;
