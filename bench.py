@@ -358,10 +358,14 @@ def run_b200(args):
         """Final framebuffer gather (rgb of every ray) to rank 0 over NCCL."""
         if world == 1:
             return
-        rgb = buf.view(n_local, 84)[:, :12].contiguous()
+        # NCCL's gather wants equal sizes; shards differ by at most one ray batch, so every rank sends max(shard) rows
+        # (its own rgb, zero-padded) and rank 0 keeps the first rgb_counts[r] rows of rank r's slice
+        rows = max(rgb_counts)
+        rgb = torch.zeros(rows, 12, dtype=torch.uint8, device="cuda")
+        rgb[:n_local] = buf.view(n_local, 84)[:, :12]
         nonlocal gather_list
         if rank == 0 and gather_list is None:
-            gather_list = [torch.empty(c, 12, dtype=torch.uint8, device="cuda") for c in rgb_counts]
+            gather_list = [torch.empty(rows, 12, dtype=torch.uint8, device="cuda") for _ in rgb_counts]
         dist.gather(rgb, gather_list if rank == 0 else None, dst=0)
 
     totals = {"queries": 0, "samples": 0, "escaped": 0, "launches": 0, "kernel_ms": 0.0}

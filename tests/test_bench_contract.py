@@ -1,4 +1,4 @@
-"""The committed bench line (profiles/r01_bench.json, written by `python bench.py` on a B200) carries every key of the
+"""The committed bench lines (profiles/r0N_bench.json, written by `python bench.py` on a B200) carries every key of the
 measurement contract, and the reference arm prints the same line shape on the CPU."""
 import json
 import subprocess
@@ -31,8 +31,9 @@ def _check(line, reference=False):
         assert 0 < line["e2e"]["value"] <= line["value"] * 1.05
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    text = (ROOT / "profiles" / "r01_bench.json").read_text().strip().splitlines()[-1]
+@pytest.mark.parametrize("name", ["r01_bench.json", "r02_bench.json"])
+def test_committed_bench_line_has_the_contract_keys(name):
+    text = (ROOT / "profiles" / name).read_text().strip().splitlines()[-1]
     _check(json.loads(text))
 
 
