@@ -72,6 +72,46 @@ struct DeviceBuffer {
 
 }  // namespace
 
+// Streams and events of the host-streaming pipeline (b200rt_trace), created on first use and kept with the scene: a
+// single-pass render of a 1440^2 stream lasts a few milliseconds end to end, stream / event creation must not be in it.
+struct StreamPipe {
+  static constexpr int kRing = 3;
+  cudaStream_t in = nullptr, out = nullptr;
+  cudaEvent_t evIn[kRing]{}, evRender[kRing]{}, evOut[kRing]{};
+  std::vector<cudaEvent_t> timing;  // pool; per tile: h2d begin, h2d end, d2h begin, d2h end
+  size_t timingUsed = 0;
+  cudaError_t init() {
+    if (in) return cudaSuccess;
+    cudaError_t e = cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking);
+    for (int i = 0; i < kRing && e == cudaSuccess; ++i) {
+      e = cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&evRender[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&evOut[i], cudaEventDisableTiming);
+    }
+    return e;
+  }
+  cudaError_t record_timing(cudaStream_t st) {
+    if (timingUsed == timing.size()) {
+      cudaEvent_t e;
+      const cudaError_t rc = cudaEventCreate(&e);
+      if (rc != cudaSuccess) return rc;
+      timing.push_back(e);
+    }
+    return cudaEventRecord(timing[timingUsed++], st);
+  }
+  void release() {
+    for (int i = 0; i < kRing; ++i)
+      for (cudaEvent_t e : {evIn[i], evRender[i], evOut[i]})
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : timing) cudaEventDestroy(e);
+    timing.clear();
+    if (in) cudaStreamDestroy(in);
+    if (out) cudaStreamDestroy(out);
+    in = out = nullptr;
+  }
+};
+
 struct b200rt_scene {
   int device = 0;
   int numSMs = 0;
@@ -84,6 +124,8 @@ struct b200rt_scene {
   DeviceBuffer nodes, pairs, leafOrig, leafInfo, geoms, triVerts, triNormals, triFaceNormals, spheres, discs, matIDs, materials;
   DeviceBuffer workCounter, counters, primA, primB;
   DeviceBuffer rays;                                   // device copy of the stream (host-buffer entry point)
+  StreamPipe pipe;
+  std::vector<cudaEvent_t> timerEvents;                // pool of the per-kernel timing events (KernelTimer), kept across calls
   DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
   DeviceBuffer wfState[2][7], wfHitA, wfHitB, wfCounts;  // wavefront path state (two slot-indexed arrays of records)
   b200rt_trace_stats stats{};
@@ -101,6 +143,8 @@ struct b200rt_scene {
       b->release();
     for (auto& set : wfState)
       for (DeviceBuffer& b : set) b.release();
+    pipe.release();
+    for (cudaEvent_t e : timerEvents) cudaEventDestroy(e);
     if (evStart) cudaEventDestroy(evStart);
     if (evStop) cudaEventDestroy(evStop);
     if (stream) cudaStreamDestroy(stream);
@@ -232,8 +276,9 @@ struct KernelTimer {
   enum Kind { TRACE = 0, NIF = 1, ACCUM = 2, SHADE = 3 };
   struct Span { cudaEvent_t a, b; Kind kind; int launches; };
   std::vector<Span> spans;
-  std::vector<cudaEvent_t> pool;
+  std::vector<cudaEvent_t>& pool;  // the scene's: creating events is host time inside short renders
   size_t used = 0;
+  explicit KernelTimer(std::vector<cudaEvent_t>& p) : pool(p) {}
   cudaEvent_t get() {
     if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
     return pool[used++];
@@ -252,7 +297,6 @@ struct KernelTimer {
     spans.clear();
     used = 0;
   }
-  ~KernelTimer() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
 };
 
 float host_tan_half_fov(float fov) {
@@ -266,6 +310,7 @@ float host_tan_half_fov(float fov) {
 struct RenderRun {
   KernelTimer timer;
   uint64_t launches = 0;
+  explicit RenderRun(b200rt_scene& sc) : timer(sc.timerEvents) {}
 };
 
 int render_begin(b200rt_scene& sc, RenderRun&) {
@@ -535,7 +580,7 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
   cudaStream_t saved = sc.stream;
   if (stream) sc.stream = stream;
   struct Restore { b200rt_scene& s; cudaStream_t v; ~Restore() { s.stream = v; } } restore{sc, saved};
-  RenderRun run;
+  RenderRun run(sc);
   if (int rc = render_begin(sc, run)) return rc;
   if (int rc = render_enqueue(sc, p, d_rays, n, run)) return rc;
   return render_end(sc, run);
@@ -756,43 +801,24 @@ int b200rt_trace(b200rt_scene* sc, const b200rt_trace_params* params, void* rays
   const size_t myBatches = firstBatch < allBatches ? (allBatches - firstBatch + stride - 1) / stride : 0;
   if (myBatches == 0) return B200RT_OK;
   static const size_t envTile = [] { const char* e = std::getenv("B200RT_TILE_RAYS"); return e ? (size_t)std::atoll(e) : (size_t)0; }();
-  // single-pass renders are bound by the PCIe copies: small tiles so that the two copy directions overlap almost
-  // completely; multi-sample renders are bound by the kernels: large tiles keep the per-bounce launches large
-  const size_t wantTile = envTile ? envTile : (sc->desc.path_trace ? (size_t)1 << 20 : (size_t)1 << 17);
+  // single-pass renders are bound by the PCIe copies: tiles small enough that the two copy directions overlap for most
+  // of the stream, large enough that the host can enqueue them faster than they drain; multi-sample renders are bound
+  // by the kernels: large tiles keep the per-bounce launches large
+  // (measured at 1440^2, 174 MB each way: 7.3 / 6.5 / 5.6 / 4.9 / 4.8 ms end to end with tiles of 32 K ... 512 K rays -- below
+  // ~256 K rays the ~20 driver calls a tile costs the host are what the pipeline waits for)
+  // 8192^2 (5.6 GB each way, PCIe floor 112 ms with both directions busy): 130 / 123 / 120 ms with 512 K / 1 M / 2 M rays.
+  const size_t singlePass = std::min<size_t>(std::max<size_t>(n / 16, (size_t)1 << 19), (size_t)1 << 21);
+  const size_t wantTile = envTile ? envTile : (sc->desc.path_trace ? (size_t)1 << 20 : singlePass);
   const size_t tileBatches = std::max<size_t>(1, wantTile / batch);
   const size_t numTiles = (myBatches + tileBatches - 1) / tileBatches;
-  constexpr int kRing = 3;
+  constexpr int kRing = StreamPipe::kRing;
   const int ring = (int)std::min<size_t>(kRing, numTiles);
   const size_t tileBytes = std::min(tileBatches, myBatches) * batch * 84;
   CU_TRY(sc->rays.reserve(tileBytes * ring));
-
-  struct Pipe {
-    cudaStream_t in = nullptr, out = nullptr;
-    cudaEvent_t evIn[kRing]{}, evRender[kRing]{}, evOut[kRing]{};
-    std::vector<cudaEvent_t> timing;  // per tile: h2d begin, h2d end, d2h begin, d2h end
-    ~Pipe() {
-      for (int i = 0; i < kRing; ++i)
-        for (cudaEvent_t e : {evIn[i], evRender[i], evOut[i]})
-          if (e) cudaEventDestroy(e);
-      for (cudaEvent_t e : timing) cudaEventDestroy(e);
-      if (in) cudaStreamDestroy(in);
-      if (out) cudaStreamDestroy(out);
-    }
-  } pipe;
-  CU_TRY(cudaStreamCreateWithFlags(&pipe.in, cudaStreamNonBlocking));
-  CU_TRY(cudaStreamCreateWithFlags(&pipe.out, cudaStreamNonBlocking));
-  for (int i = 0; i < ring; ++i) {
-    CU_TRY(cudaEventCreateWithFlags(&pipe.evIn[i], cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&pipe.evRender[i], cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&pipe.evOut[i], cudaEventDisableTiming));
-  }
-  auto timing_event = [&](cudaStream_t st) -> cudaError_t {
-    cudaEvent_t e;
-    cudaError_t rc = cudaEventCreate(&e);
-    if (rc != cudaSuccess) return rc;
-    pipe.timing.push_back(e);
-    return cudaEventRecord(e, st);
-  };
+  StreamPipe& pipe = sc->pipe;
+  CU_TRY(pipe.init());
+  pipe.timingUsed = 0;
+  auto timing_event = [&](cudaStream_t st) -> cudaError_t { return pipe.record_timing(st); };
   std::vector<CallbackJob> jobs;
   if (cb) jobs.resize(myBatches);
   // rays of my j-th batch
@@ -800,7 +826,7 @@ int b200rt_trace(b200rt_scene* sc, const b200rt_trace_params* params, void* rays
   auto batch_len = [&](size_t j) { return std::min(batch, n - batch_lo(j)); };
 
   const auto t0 = std::chrono::steady_clock::now();
-  RenderRun run;
+  RenderRun run(*sc);
   if (int rc = render_begin(*sc, run)) return rc;
   for (size_t k = 0; k < numTiles; ++k) {
     const int slot = (int)(k % (size_t)ring);
@@ -846,7 +872,7 @@ int b200rt_trace(b200rt_scene* sc, const b200rt_trace_params* params, void* rays
   if (int rc = render_end(*sc, run)) return rc;
   sc->stats.trace_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   // copy time = sum over tiles (the copies of different tiles overlap the kernels, not each other)
-  for (size_t i = 0; i + 4 <= pipe.timing.size(); i += 4) {
+  for (size_t i = 0; i + 4 <= pipe.timingUsed; i += 4) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, pipe.timing[i], pipe.timing[i + 1]) == cudaSuccess) sc->stats.h2d_ms += ms;
     if (cudaEventElapsedTime(&ms, pipe.timing[i + 2], pipe.timing[i + 3]) == cudaSuccess) sc->stats.d2h_ms += ms;
