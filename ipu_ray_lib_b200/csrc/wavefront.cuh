@@ -85,7 +85,18 @@ __device__ __forceinline__ void wf_camera_path(const WfArgs& a, uint32_t p, V3& 
 enum : uint32_t { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2 };
 // measured on the B200 (scripts/wf_kernel_times.py, 1.940 / 1.888 / 1.938 ms per launch at 8 / 12 / 16); the scheduler
 // model (scripts/wf_sched_sim.cpp) has its optimum at the same place
-constexpr int kTravThreshold = 12;
+#ifndef B200RT_TRAV_THRESHOLD
+#define B200RT_TRAV_THRESHOLD 12
+#endif
+#ifndef B200RT_TRAV_THRESHOLD_FIRST
+#define B200RT_TRAV_THRESHOLD_FIRST B200RT_TRAV_THRESHOLD
+#endif
+#ifndef B200RT_WF_CLAIM
+#define B200RT_WF_CLAIM 128
+#endif
+#ifndef B200RT_SHADE_BLOCKS
+#define B200RT_SHADE_BLOCKS 6
+#endif
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -111,6 +122,7 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[a.qIn ^ 1] = 0u;
   Counters cnt = {0u, 0u};
   unsigned nClosest = 0;
+  constexpr int kTravThreshold = kFirst ? B200RT_TRAV_THRESHOLD_FIRST : B200RT_TRAV_THRESHOLD;
 
   StreamQuery q;  // the lane's query
   q.o = q.op = q.inv = mk(0.f, 0.f, 0.f); q.d = mk(0.f, 0.f, -1.f);
@@ -120,7 +132,7 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
   uint32_t slot = 0xFFFFFFFFu;  // the slot whose query this is; none before the first fetch
   uint2 stack[kMaxStack + 1];   // deferred children below the register-held top: {reference, entry distance}
   // slots are claimed kClaim at a time per warp: one same-address atomic per 128 rays
-  constexpr uint32_t kClaim = 128;
+  constexpr uint32_t kClaim = B200RT_WF_CLAIM;
   uint32_t wNext = 0, wEnd = 0;  // warp-uniform: the unclaimed part of this warp's current batch
   unsigned phaseIters[3] = {0u, 0u, 0u}, phaseLanes[3] = {0u, 0u, 0u};  // kCount builds: scheduler statistics
 
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
 // per 256 paths and array.
 // 6 blocks per SM (40 registers): the kernel waits on dependent loads (hit -> leafInfo -> vertices -> material), so it is
 // occupancy that buys time here; measured 1.6 ms per launch at 1 block's worth of registers, 1.0 at 4-8.
-constexpr int kShadeBlocksPerSM = 6;
+constexpr int kShadeBlocksPerSM = B200RT_SHADE_BLOCKS;
 template <bool kNif, bool kFirst>
 __global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const WfArgs a) {
   const TraceArgs& t = a.t;

@@ -159,3 +159,29 @@ def test_nif_lit_path_trace_matches_oracle(port, name, chunk):
     # per-pixel: allow the rare fp16 argument flip caused by libm-vs-CUDA acos/atan2 ulp differences
     rel = np.abs(got["rgb"] - want["rgb"]).max(axis=1) / np.maximum(np.abs(want["rgb"]).max(axis=1), 1e-6)
     assert np.mean(rel > MAX_REL) < 5e-3
+
+
+@pytest.mark.gpu
+def test_config2_nif_lit_window_of_the_full_frame(port):
+    """BASELINE.json config 2 WITH its environment light on a 1440 x 48 window of the 1440 x 1440 frame (seed 1442,
+    synthetic weights of seed 1442, the bench's model): hit records bit-exact, rgb within the stated NIF tolerance,
+    escaped-sample count equal to the oracle's."""
+    from ipu_ray_lib_b200.render import B200Scene
+    spp = 6
+    s = scene.HostScene.builtin("box").configure(1440, 1440, path_trace=True, samples=spp, seed=1442)
+    nif = NifWeights.synthetic(seed=1442)
+    base = scene.init_ray_stream(1440, 1440, s.fov, window=(1440, 48, 0, 696))
+    want = base.copy()
+    cw = port.path_trace(s, want, nif=nif)
+    with B200Scene(s) as g:
+        g.load_nif_model(nif)
+        got = base.copy()
+        g.execute(got)
+        st = g.stats()
+    assert st["escaped_samples"] == cw["escaped_samples"] and st["closest_hit_queries"] == cw["closest_hit_queries"]
+    a = got.copy(); b = want.copy()
+    a["rgb"] = 0; b["rgb"] = 0
+    assert a.tobytes() == b.tobytes()
+    assert np.abs(got["rgb"].astype(np.float64) - want["rgb"]).sum() / np.abs(want["rgb"]).sum() < MEAN_REL
+    rel = np.abs(got["rgb"] - want["rgb"]).max(axis=1) / np.maximum(np.abs(want["rgb"]).max(axis=1), 1e-6)
+    assert np.mean(rel > MAX_REL) < 5e-3
