@@ -493,11 +493,11 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
             timer.end(sc.stream);
             timer.begin(KernelTimer::SHADE, sc.stream);
             if (sc.nif) {
-              if (first) rt::wf_shade_kernel<true, true><<<gridSmall, 256, 0, sc.stream>>>(w);
-              else rt::wf_shade_kernel<true, false><<<gridSmall, 256, 0, sc.stream>>>(w);
+              if (first) rt::wf_shade_kernel<true, true><<<gridSmall, rt::kShadeThreads, 0, sc.stream>>>(w);
+              else rt::wf_shade_kernel<true, false><<<gridSmall, rt::kShadeThreads, 0, sc.stream>>>(w);
             } else {
-              if (first) rt::wf_shade_kernel<false, true><<<gridSmall, 256, 0, sc.stream>>>(w);
-              else rt::wf_shade_kernel<false, false><<<gridSmall, 256, 0, sc.stream>>>(w);
+              if (first) rt::wf_shade_kernel<false, true><<<gridSmall, rt::kShadeThreads, 0, sc.stream>>>(w);
+              else rt::wf_shade_kernel<false, false><<<gridSmall, rt::kShadeThreads, 0, sc.stream>>>(w);
             }
             timer.end(sc.stream);
             CU_TRY(cudaGetLastError());

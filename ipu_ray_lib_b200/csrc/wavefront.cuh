@@ -94,9 +94,27 @@ enum : uint32_t { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2 };
 #ifndef B200RT_WF_CLAIM
 #define B200RT_WF_CLAIM 128
 #endif
+#ifndef B200RT_SHADE_PREFETCH
+#define B200RT_SHADE_PREFETCH 1
+#endif
+#ifndef B200RT_TRACE_PREFETCH
+#define B200RT_TRACE_PREFETCH 0
+#endif
+#ifndef B200RT_SHADE_STREAMING_HINTS
+#define B200RT_SHADE_STREAMING_HINTS 1
+#endif
+#if B200RT_SHADE_STREAMING_HINTS
+#define WF_LD(p) __ldcs(p)
+#define WF_ST(p, v) __stcs(p, v)
+#else
+#define WF_LD(p) (*(p))
+#define WF_ST(p, v) (*(p) = (v))
+#endif
 #ifndef B200RT_SHADE_BLOCKS
 #define B200RT_SHADE_BLOCKS 6
 #endif
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -191,6 +209,15 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
         if (lane == 0) claimBase = atomicAdd(cursor, kClaim);
         wNext = __shfl_sync(full, claimBase, 0);
         wEnd = wNext + kClaim;
+#if B200RT_TRACE_PREFETCH
+        if (!kFirst) {
+#pragma unroll
+          for (uint32_t k = 0; k < kClaim; k += 32u) {
+            const uint32_t s = wNext + k + lane;
+            if (s < count) { prefetch_l2(in.rayO + s); prefetch_l2(in.rayI + s); prefetch_l2(in.rayS + s); }
+          }
+        }
+#endif
       }
       const uint32_t avail = wEnd - wNext;
       const uint32_t rank = (uint32_t)__popc(mF & ((1u << lane) - 1u));
@@ -245,9 +272,14 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
 // per 256 paths and array.
 // 6 blocks per SM (40 registers): the kernel waits on dependent loads (hit -> leafInfo -> vertices -> material), so it is
 // occupancy that buys time here; measured 1.6 ms per launch at 1 block's worth of registers, 1.0 at 4-8.
-constexpr int kShadeBlocksPerSM = B200RT_SHADE_BLOCKS;
+#ifndef B200RT_SHADE_THREADS
+#define B200RT_SHADE_THREADS 128
+#endif
+constexpr int kShadeThreads = B200RT_SHADE_THREADS;  // 256, 128 or 64: the warps of a block share its two barriers per round
+constexpr int kShadeWarps = kShadeThreads / 32;
+constexpr int kShadeBlocksPerSM = B200RT_SHADE_BLOCKS * (256 / kShadeThreads);
 template <bool kNif, bool kFirst>
-__global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const WfArgs a) {
+__global__ void __launch_bounds__(kShadeThreads, kShadeBlocksPerSM) wf_shade_kernel(const WfArgs a) {
   const TraceArgs& t = a.t;
   const DevScene& sc = t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
@@ -259,7 +291,7 @@ __global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const 
   if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[2] = 0u;
   unsigned nSamples = 0, nEscaped = 0;
   __shared__ uint32_t sCountBuf[2][2][8];  // [round parity][queue][warp]: the next round posts into the other half
-  static_assert(256 / 32 == 8, "block-level append assumes 8 warps");
+  static_assert(kShadeWarps == 8 || kShadeWarps == 4 || kShadeWarps == 2, "block-level append: 2, 4 or 8 warps");
   // whole blocks iterate together (uniform trip count) so the ballots and barriers below see converged threads
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t rounds = (count + stride - 1) / stride;
@@ -267,6 +299,13 @@ __global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const 
     uint32_t (*sCount)[8] = sCountBuf[r & 1u];
     const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < count;
+#if B200RT_SHADE_PREFETCH
+    // the records of the block's next round are on their way from DRAM to L2 while this round is shaded
+    if (i + stride < count) {
+      prefetch_l2(a.b.hitA + i + stride);
+      if (!kFirst) { prefetch_l2(in.rayO + i + stride); prefetch_l2(in.rayD + i + stride); prefetch_l2(in.thr + i + stride); prefetch_l2(in.rng + i + stride); }
+    }
+#endif
     bool survive = false, lastOne = false;
     uint32_t appendSlot = 0xFFFFFFFFu, p = 0;
     // the survivor's next record, held in registers until its slot is known
@@ -275,7 +314,7 @@ __global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const 
     Rng rng;
     rng.s0 = rng.s1 = 0ull;
     if (valid) {
-      const float2 ha = a.b.hitA[i];
+      const float2 ha = WF_LD(a.b.hitA + i);
       Hit hit;
       hit.t = ha.x;
       stream_hit_ids(sc, __float_as_uint(ha.y), hit.geomID, hit.primID, hit.tri);
@@ -285,8 +324,8 @@ __global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const 
         p = i;
         wf_camera_path(a, p, o, d, rng);  // same ray, same RNG state as the trace kernel started from
       } else {
-        const float4 ro = in.rayO[i], rd = in.rayD[i], th = in.thr[i];
-        const uint4 rs = in.rng[i];
+        const float4 ro = WF_LD(in.rayO + i), rd = WF_LD(in.rayD + i), th = WF_LD(in.thr + i);
+        const uint4 rs = WF_LD(in.rng + i);
         p = __float_as_uint(th.w);
         o = mk(ro.x, ro.y, ro.z); d = mk(rd.x, rd.y, rd.z);
         thr = mk(th.x, th.y, th.z);
@@ -391,7 +430,7 @@ __global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const 
       if (warp == 0) {
         // exclusive scan of the 8 warp counts of each queue in lanes 0..7 / 8..15
         const int q = lane >> 3, w = lane & 7;
-        uint32_t v = lane < 16 ? sCount[q][w] : 0u, incl = v;
+        uint32_t v = (lane < 16 && w < kShadeWarps) ? sCount[q][w] : 0u, incl = v;
 #pragma unroll
         for (int off = 1; off < 8; off <<= 1) {
           const uint32_t up = __shfl_up_sync(full, incl, off, 8);
@@ -407,18 +446,18 @@ __global__ void __launch_bounds__(256, kShadeBlocksPerSM) wf_shade_kernel(const 
       if (survive) {
         // consecutive survivors of a warp write consecutive records: full sectors
         const uint32_t j = sCount[0][warp] + __popc(mS & ((1u << lane) - 1u));
-        out.rayO[j] = make_float4(o.x, o.y, o.z, __uint_as_float(bounce | (flags << 8) | (geomID << 16)));
-        out.rayD[j] = make_float4(d.x, d.y, d.z, __uint_as_float(primID));
-        out.thr[j] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(p));
-        out.rng[j] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
+        WF_ST(out.rayO + j, make_float4(o.x, o.y, o.z, __uint_as_float(bounce | (flags << 8) | (geomID << 16))));
+        WF_ST(out.rayD + j, make_float4(d.x, d.y, d.z, __uint_as_float(primID)));
+        WF_ST(out.thr + j, make_float4(thr.x, thr.y, thr.z, __uint_as_float(p)));
+        WF_ST(out.rng + j, make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32)));
         if (lastOne) out.nrm[j] = make_float4(n.x, n.y, n.z, 0.f);
         // constants of the next query, computed here where every lane has a ray (wf_trace's fetch phase runs at ~20 lanes)
         V3 inv;
         float sx, sy, sz;
         uint32_t qflags;
         stream_prepare(sc, o, d, inv, sx, sy, sz, qflags);
-        out.rayI[j] = make_float4(inv.x, inv.y, inv.z, 0.f);
-        out.rayS[j] = make_float4(sx, sy, sz, __uint_as_float(qflags));
+        WF_ST(out.rayI + j, make_float4(inv.x, inv.y, inv.z, 0.f));
+        WF_ST(out.rayS + j, make_float4(sx, sy, sz, __uint_as_float(qflags)));
       }
       if (kNif && appendSlot != 0xFFFFFFFFu) t.escapeQueue[sCount[1][warp] + __popc(mE & ((1u << lane) - 1u))] = appendSlot;
       // no third barrier: the next round posts its counts into the other half of sCountBuf, and a warp can only get

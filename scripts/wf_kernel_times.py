@@ -1,5 +1,6 @@
 """A/B aid: per-kernel device times (the library's own CUDA-event spans) of the wavefront tracer on the bench scene,
 without the NIF stage, repeated; prints min / median per launch so that builds can be compared below the run-to-run noise."""
+import os
 import sys
 import numpy as np
 import torch
@@ -14,11 +15,12 @@ rays = init_ray_stream(1440, 1440, s.fov)
 dev = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
 pristine = dev.clone()
 tr, sh = [], []
+extra = {'scene_residency': int(os.environ['WF_RESIDENCY'])} if 'WF_RESIDENCY' in os.environ else {}
 with B200Scene(s) as g:
     for r in range(reps + 2):
         dev.copy_(pristine)
         torch.cuda.synchronize()
-        g.execute_device(dev.data_ptr(), rays.size, stream=torch.cuda.current_stream().cuda_stream)
+        g.execute_device(dev.data_ptr(), rays.size, stream=torch.cuda.current_stream().cuda_stream, **extra)
         torch.cuda.synchronize()
         st = g.stats()
         if r >= 2:
