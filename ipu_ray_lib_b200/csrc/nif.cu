@@ -337,7 +337,10 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   if (m->tcOk) {
     const uint32_t tcTiles = (count + tc::kRows - 1) / tc::kRows;
-    const uint32_t tcGrid = tcTiles < (uint32_t)sms ? (tcTiles ? tcTiles : 1u) : (uint32_t)sms;  // one persistent CTA per SM
+    // one persistent CTA per SM; B200RT_NIF_GRID caps the number of CTAs (measurements: how the kernel scales with SMs)
+    static const uint32_t envGrid = [] { const char* e = std::getenv("B200RT_NIF_GRID"); return e ? (uint32_t)std::atoi(e) : 0u; }();
+    const uint32_t maxGrid = envGrid ? std::min(envGrid, (uint32_t)sms) : (uint32_t)sms;
+    const uint32_t tcGrid = tcTiles < maxGrid ? (tcTiles ? tcTiles : 1u) : maxGrid;
     static const bool profile = [] { const char* e = std::getenv("B200RT_NIF_PROFILE"); return e && e[0] == '1'; }();
     tc::Params params = m->tc;
     unsigned long long* dProf = nullptr;

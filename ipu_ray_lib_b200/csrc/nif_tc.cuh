@@ -25,12 +25,13 @@
 //       while B0/B1 run the epilogue drains N1 straight into the hi columns               -> next layer's B2/B3 may start.
 // In-place update stays safe (nothing is stored into X before all MMAs of the layer have completed), and no MMA
 // ever targets a TMEM slot that is still being drained (the third slot).
-// Measured limits (B200, 148 CTAs): the kernel moves 416 GB of weights L2 -> SM per 45.7 M rows (every CTA re-streams the
-// 1.16 MB of weights per 128-row tile) = 39.7 B/cycle/SM = ~6000 B/cycle chip-wide, which IS the L2 slice throughput
-// cap (~6100-6300 B/cycle); TMEM drains at 64 B/cycle/SM (2560 cycles per layer against 3360 cycles of MMAs). Variants
-// that hide the epilogue completely (128/192 column split, double-buffered lo columns, feature encode on dedicated
-// warps; kept under scripts/experiments/) remove the layer-boundary bubbles but then wait for weights instead: 28 K
-// cycles per tile either way. The next step is structural: cta_group::2 CTA pairs, each SM loading half of B.
+// Measured limits (B200): every CTA re-streams the 1.16 MB of weights per 128-row tile, 28.4 K cycles per tile =
+// 41 B/cycle/SM against ~42.6 B/cycle/SM of L2 -> SM read rate (6300 B/cycle chip-wide over 148 SMs). The cap is per
+// SM: with 74 ... 148 CTAs (B200RT_NIF_GRID) the cycles per tile do not move (profiles/r02_nif_grid.txt). TMEM drains
+// at 64 B/cycle/SM (2560 cycles per layer against 3360 cycles of MMAs). Variants that hide the epilogue completely
+// (128/192 column split, double-buffered lo columns, feature encode on dedicated warps; kept under
+// scripts/experiments/) remove the layer-boundary bubbles but then wait for weights instead: 28 K cycles per tile
+// either way. The next step is structural (fewer weight bytes per row): cta_group::2 CTA pairs, each SM loading half of B.
 // Roles: warps 0-7 = encode + epilogue, warp 8 lane 0 = weight producer, warp 9 = MMA issuer (whole warp converged,
 // one elected lane issues, so descriptors stay in uniform registers).
 #pragma once

@@ -112,6 +112,19 @@ class NifWeights:
         return sum(2 * l.kernel.shape[0] * l.kernel.shape[1] + (l.kernel.shape[1] if l.bias is not None else 0)
                    for l in self.layers)
 
+    def weight_stream_bytes_per_tile(self) -> int:
+        """fp16 bytes of weight images one 128-row tile of the tensor-core kernel streams from L2 (csrc/nif_tc.cuh): per
+        layer (K rounded up to 16 + one 16-row bias slice) x (N padded to 16, hidden widths to 160 or 320) x 2 B."""
+        total = 0
+        for l in self.layers:
+            k, n = l.kernel.shape
+            kpad = (k + 15) // 16 * 16 + 16
+            npad = (n + 15) // 16 * 16
+            if npad > 16:
+                npad = 160 if npad <= 160 else 320
+            total += kpad * npad * 2
+        return total
+
     def to_desc(self):
         """(b200rt_nif_desc, keepalive) for the C ABI / oracle."""
         n = len(self.layers)
