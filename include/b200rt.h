@@ -106,7 +106,12 @@ typedef struct b200rt_trace_params {
                                 * R threads without regrouping it. The callback's batch_index is the batch's index in
                                 * the whole stream (= k * R + replica, src/RayCallback.cpp:8-24) */
   uint32_t first_batch;
-  uint32_t reserved[2];
+  uint32_t tail_bounce;        /* wavefront path tracer: the bounces from this one on run in ONE cooperative launch
+                                * (trace phase, grid barrier, shade phase, grid barrier, ... until no path is left) instead
+                                * of two launches per bounce. 0 = auto (roulette_start_depth + 2: with Russian roulette the
+                                * paths still alive by then are a fraction of a per cent of a chunk), 1 = never (one trace
+                                * and one shade launch per bounce), N >= 2 = from bounce N. Same results either way */
+  uint32_t reserved[1];
 } b200rt_trace_params;
 
 /* Counters of the last trace (device-side counted, exact). */

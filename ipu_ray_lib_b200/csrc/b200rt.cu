@@ -116,6 +116,7 @@ struct b200rt_scene {
   int device = 0;
   int numSMs = 0;
   int maxSmemOptin = 0;
+  bool cooperativeLaunch = false;  // wf_tail_kernel needs grid-wide barriers
   cudaStream_t stream = nullptr;
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   b200rt_scene_desc desc{};  // scalars only are used after creation
@@ -468,7 +469,32 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
           static const bool envPhase = std::getenv("B200RT_WF_PHASE_STATS") != nullptr;
           unsigned long long* dPhase = nullptr;
           if (envPhase && L.count) { cudaMalloc(&dPhase, 16 * 6 * 8); cudaMemsetAsync(dPhase, 0, 16 * 6 * 8, sc.stream); }
+          // Bounces from tailStart on run in one cooperative launch (wf_tail_kernel): with Russian roulette the paths alive
+          // two bounces after it starts are a fraction of a per cent of the chunk. B200RT_WF_TAIL overrides params.tail_bounce (1 = off, N = from bounce N) for A/B runs.
+          static const int envTail = [] { const char* e = std::getenv("B200RT_WF_TAIL"); return e ? std::atoi(e) : -1; }();
+          const uint32_t tailWanted = envTail >= 0 ? (uint32_t)envTail : p.tail_bounce;  // 0 = auto, 1 = never, N = from bounce N
+          uint32_t tailStart = tailWanted == 0u ? sc.desc.roulette_start_depth + 2u : tailWanted;
+          if (tailStart < 2u || tailStart + 2u > sc.desc.max_path_length || dPhase || !sc.cooperativeLaunch) tailStart = 0xFFFFFFFFu;
           for (uint32_t b = 0; b < sc.desc.max_path_length; ++b) {
+            if (b == tailStart) {
+              w.qIn = (int)(b & 1u);
+              w.phaseStats = nullptr;
+              uint32_t bounceBegin = b, bounceEnd = sc.desc.max_path_length;
+              void* kargs[] = {&w, &bounceBegin, &bounceEnd};
+              const void* fn;
+              const bool nifOn = sc.nif != nullptr;
+              if (L.shared) fn = L.count ? (nifOn ? (const void*)rt::wf_tail_kernel<true, true, true> : (const void*)rt::wf_tail_kernel<true, true, false>)
+                                         : (nifOn ? (const void*)rt::wf_tail_kernel<true, false, true> : (const void*)rt::wf_tail_kernel<true, false, false>);
+              else fn = L.count ? (nifOn ? (const void*)rt::wf_tail_kernel<false, true, true> : (const void*)rt::wf_tail_kernel<false, true, false>)
+                                : (nifOn ? (const void*)rt::wf_tail_kernel<false, false, true> : (const void*)rt::wf_tail_kernel<false, false, false>);
+              const size_t tailSmem = L.shared ? L.smem : 0;
+              if (tailSmem) CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tailSmem));
+              timer.begin(KernelTimer::TRACE, sc.stream);
+              CU_TRY(cudaLaunchCooperativeKernel(fn, dim3((unsigned)sc.numSMs), dim3(1024), kargs, tailSmem, sc.stream));
+              timer.end(sc.stream);
+              launches += 1;
+              break;
+            }
             w.qIn = (int)(b & 1u);
             w.phaseStats = dPhase ? dPhase + 6 * std::min<uint32_t>(b, 15u) : nullptr;
             // no memsets between the kernels: wf_trace empties the counter its wf_shade appends to, wf_shade resets the
@@ -638,6 +664,7 @@ int b200rt_scene_create(const b200rt_scene_desc* d, b200rt_scene** out) {
   sc->desc = *d;
   CU_TRY(cudaDeviceGetAttribute(&sc->numSMs, cudaDevAttrMultiProcessorCount, device));
   CU_TRY(cudaDeviceGetAttribute(&sc->maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  { int coop = 0; CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device)); sc->cooperativeLaunch = coop != 0; }
   CU_TRY(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
   CU_TRY(cudaEventCreate(&sc->evStart));
   CU_TRY(cudaEventCreate(&sc->evStop));
@@ -827,6 +854,11 @@ int b200rt_trace(b200rt_scene* sc, const b200rt_trace_params* params, void* rays
 
   const auto t0 = std::chrono::steady_clock::now();
   RenderRun run(*sc);
+  // an early error return must not leave copies, kernels or queued callbacks (which point into `jobs`) in flight
+  struct Drain {
+    b200rt_scene& s; bool armed = true;
+    ~Drain() { if (armed) { cudaStreamSynchronize(s.pipe.in); cudaStreamSynchronize(s.stream); cudaStreamSynchronize(s.pipe.out); } }
+  } drain{*sc};
   if (int rc = render_begin(*sc, run)) return rc;
   for (size_t k = 0; k < numTiles; ++k) {
     const int slot = (int)(k % (size_t)ring);
@@ -870,6 +902,7 @@ int b200rt_trace(b200rt_scene* sc, const b200rt_trace_params* params, void* rays
   }
   CU_TRY(cudaStreamSynchronize(pipe.out));
   if (int rc = render_end(*sc, run)) return rc;
+  drain.armed = false;
   sc->stats.trace_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   // copy time = sum over tiles (the copies of different tiles overlap the kernels, not each other)
   for (size_t i = 0; i + 4 <= pipe.timingUsed; i += 4) {

@@ -686,7 +686,7 @@ RT_HD bool stream_leaf(const DevScene& sc, StreamQuery& q, const uint2* stack, c
     t = t > 0.f ? t : __builtin_huge_valf();  // Mesh.hpp:90-93: only t > 0 replaces the inf default
   } else {
     V3 d = q.d;
-    if (lazyD) { const float4 dd = RT_LDG(lazyD); d = mk(dd.x, dd.y, dd.z); }
+    if (lazyD) { const float4 dd = *lazyD; d = mk(dd.x, dd.y, dd.z); }  // path state: never through the non-coherent path
     if (type == 1u) t = sphere_test(RT_LDG(sc.spheres + index), q.o, d, 0.f);
     else t = disc_test(sc.discs + 7u * index, q.o, d);
   }

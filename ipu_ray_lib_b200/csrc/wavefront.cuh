@@ -18,6 +18,7 @@
 // The arithmetic per path is the megakernel's, statement for statement, so results are bit-identical; only the
 // grouping of work changes. rgb is accumulated afterwards in sample order by wf_accumulate_kernel.
 #pragma once
+#include <cooperative_groups.h>
 #include "trace_kernels.cuh"
 
 namespace rt {
@@ -122,22 +123,19 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
+// The kernel's body: one bounce's queries for the CTA's warps. `pairs` / `pairsShared` = the pair table (staged copy and
+// its shared-window address when kShared). Called by wf_trace_kernel (one launch per bounce) and by wf_tail_kernel.
 template <bool kShared, bool kCount, bool kFirst>
-__global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
-  const uint4* pairs = stage_pairs<kShared>(a.t, reinterpret_cast<uint4*>(smemRaw));
-  // Shared-window address of the staged table, made opaque to the compiler: sm_100 materialises a shared symbol's
-  // address as (CTA rank in cluster << 24 | offset) with an S2R, and would redo that in every inner-node step.
-  uint32_t pairsShared = kShared ? (uint32_t)__cvta_generic_to_shared(smemRaw) : 0u;
-  asm volatile("" : "+r"(pairsShared));
+__device__ __forceinline__ void wf_trace_body(const WfArgs& a, const int qIn, const uint4* pairs, const uint32_t pairsShared,
+                                              unsigned long long* phaseStats) {
   const DevScene& sc = a.t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
   // bounce 0 (kFirst): slot = path over all paths of the chunk and the rays are the camera rays
-  const WfState& in = a.b.st[a.qIn];
-  const uint32_t count = kFirst ? a.numPaths : a.b.counts[a.qIn];
+  const WfState& in = a.b.st[qIn];
+  const uint32_t count = kFirst ? a.numPaths : __ldcg(a.b.counts + qIn);
   uint32_t* cursor = a.b.counts + 2;
   // the shading kernel that follows appends its survivors to the other array: empty it (nobody reads that counter here)
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[a.qIn ^ 1] = 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[qIn ^ 1] = 0u;
   Counters cnt = {0u, 0u};
   unsigned nClosest = 0;
   constexpr int kTravThreshold = kFirst ? B200RT_TRAV_THRESHOLD_FIRST : B200RT_TRAV_THRESHOLD;
@@ -168,7 +166,7 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
       cL = __popc(mL); cF = __popc(mF);
       if (!(cT >= cL && cT >= cF)) pick = cL >= cF ? WF_LEAF : WF_FETCH;
     }
-    if (kCount && a.phaseStats && lane == 0 && pick != WF_TRAV) {
+    if (kCount && phaseStats && lane == 0 && pick != WF_TRAV) {
       phaseIters[pick] += 1u;
       phaseLanes[pick] += (unsigned)(pick == WF_LEAF ? cL : cF);
     }
@@ -178,7 +176,7 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
       // inner-node steps, one after the other while enough lanes want one: the loop votes for itself, so a run of steps
       // pays for one ballot each instead of a trip through the phase selection above
       do {
-        if (kCount && a.phaseStats && lane == 0) { phaseIters[WF_TRAV] += 1u; phaseLanes[WF_TRAV] += (unsigned)cT; }
+        if (kCount && phaseStats && lane == 0) { phaseIters[WF_TRAV] += 1u; phaseLanes[WF_TRAV] += (unsigned)cT; }
         again = false;
         if (wantT) {
           PairWords w;
@@ -259,9 +257,25 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
     // lane's next pop (inside the phases the compiler would move it into place at once and wait for it)
     while (again) again = stream_pop(q, stack);
   }
-  if (kCount && a.phaseStats && lane == 0)
-    for (int k = 0; k < 3; ++k) { atomicAdd(a.phaseStats + 2 * k, (unsigned long long)phaseIters[k]); atomicAdd(a.phaseStats + 2 * k + 1, (unsigned long long)phaseLanes[k]); }
+  if (kCount && phaseStats && lane == 0)
+    for (int k = 0; k < 3; ++k) { atomicAdd(phaseStats + 2 * k, (unsigned long long)phaseIters[k]); atomicAdd(phaseStats + 2 * k + 1, (unsigned long long)phaseLanes[k]); }
   flush_counters(a.t.counters, nClosest, 0u, cnt, 0u, 0u);
+}
+
+// Shared-window address of the staged table, made opaque to the compiler: sm_100 materialises a shared symbol's
+// address as (CTA rank in cluster << 24 | offset) with an S2R, and would redo that in every inner-node step.
+template <bool kShared>
+__device__ __forceinline__ uint32_t opaque_shared_base(const void* smemRaw) {
+  uint32_t base = kShared ? (uint32_t)__cvta_generic_to_shared(smemRaw) : 0u;
+  asm volatile("" : "+r"(base));
+  return base;
+}
+
+template <bool kShared, bool kCount, bool kFirst>
+__global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const uint4* pairs = stage_pairs<kShared>(a.t, reinterpret_cast<uint4*>(smemRaw));
+  wf_trace_body<kShared, kCount, kFirst>(a, a.qIn, pairs, opaque_shared_base<kShared>(smemRaw), a.phaseStats);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -278,25 +292,26 @@ __global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
 constexpr int kShadeThreads = B200RT_SHADE_THREADS;  // 256, 128 or 64: the warps of a block share its two barriers per round
 constexpr int kShadeWarps = kShadeThreads / 32;
 constexpr int kShadeBlocksPerSM = B200RT_SHADE_BLOCKS * (256 / kShadeThreads);
-template <bool kNif, bool kFirst>
-__global__ void __launch_bounds__(kShadeThreads, kShadeBlocksPerSM) wf_shade_kernel(const WfArgs a) {
+// The kernel's body for blocks of kWarps warps (2, 4 or 8: wf_shade_kernel; 32: wf_tail_kernel). sCountBuf is the
+// block's [round parity][queue][warp] scratch: the next round posts into the other half.
+template <bool kNif, bool kFirst, int kWarps>
+__device__ __forceinline__ void wf_shade_body(const WfArgs& a, const int qIn, uint32_t (*sCountBuf)[2][kWarps < 8 ? 8 : kWarps]) {
   const TraceArgs& t = a.t;
   const DevScene& sc = t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
-  const WfState& in = a.b.st[a.qIn];
-  const WfState& out = a.b.st[a.qIn ^ 1];
-  const uint32_t count = kFirst ? a.numPaths : a.b.counts[a.qIn];
-  uint32_t* countOut = a.b.counts + (a.qIn ^ 1);
+  const WfState& in = a.b.st[qIn];
+  const WfState& out = a.b.st[qIn ^ 1];
+  const uint32_t count = kFirst ? a.numPaths : __ldcg(a.b.counts + qIn);
+  uint32_t* countOut = a.b.counts + (qIn ^ 1);
   // the next trace kernel starts fetching at slot 0 again (this bounce's trace kernel is done with the cursor)
   if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[2] = 0u;
   unsigned nSamples = 0, nEscaped = 0;
-  __shared__ uint32_t sCountBuf[2][2][8];  // [round parity][queue][warp]: the next round posts into the other half
-  static_assert(kShadeWarps == 8 || kShadeWarps == 4 || kShadeWarps == 2, "block-level append: 2, 4 or 8 warps");
+  static_assert(kWarps == 32 || kWarps == 8 || kWarps == 4 || kWarps == 2, "block-level append: 2, 4, 8 or 32 warps");
   // whole blocks iterate together (uniform trip count) so the ballots and barriers below see converged threads
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t rounds = (count + stride - 1) / stride;
   for (uint32_t r = 0; r < rounds; ++r) {
-    uint32_t (*sCount)[8] = sCountBuf[r & 1u];
+    uint32_t (*sCount)[kWarps < 8 ? 8 : kWarps] = sCountBuf[r & 1u];
     const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < count;
 #if B200RT_SHADE_PREFETCH
@@ -428,19 +443,37 @@ __global__ void __launch_bounds__(kShadeThreads, kShadeBlocksPerSM) wf_shade_ker
       if (lane == 0) { sCount[0][warp] = (uint32_t)__popc(mS); sCount[1][warp] = (uint32_t)__popc(mE); }
       __syncthreads();
       if (warp == 0) {
-        // exclusive scan of the 8 warp counts of each queue in lanes 0..7 / 8..15
-        const int q = lane >> 3, w = lane & 7;
-        uint32_t v = (lane < 16 && w < kShadeWarps) ? sCount[q][w] : 0u, incl = v;
+        if (kWarps <= 8) {
+          // exclusive scan of the (up to) 8 warp counts of each queue in lanes 0..7 / 8..15
+          const int q = lane >> 3, w = lane & 7;
+          uint32_t v = (lane < 16 && w < kWarps) ? sCount[q][w] : 0u, incl = v;
 #pragma unroll
-        for (int off = 1; off < 8; off <<= 1) {
-          const uint32_t up = __shfl_up_sync(full, incl, off, 8);
-          if (w >= off) incl += up;
+          for (int off = 1; off < 8; off <<= 1) {
+            const uint32_t up = __shfl_up_sync(full, incl, off, 8);
+            if (w >= off) incl += up;
+          }
+          uint32_t base = 0;
+          if (lane == 7 && incl) base = atomicAdd(countOut, incl);
+          if (lane == 15 && incl) base = atomicAdd(t.escapeCount, incl);
+          base = __shfl_sync(full, base, (lane & 8) | 7, 32);
+          if (lane < 16) sCount[q][w] = base + incl - v;
+        } else {
+          // 32 warps: one scan per queue over all lanes
+#pragma unroll
+          for (int q = 0; q < (kNif ? 2 : 1); ++q) {
+            const uint32_t v = sCount[q][lane];
+            uint32_t incl = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+              const uint32_t up = __shfl_up_sync(full, incl, off);
+              if ((int)lane >= off) incl += up;
+            }
+            uint32_t base = 0;
+            if (lane == 31 && incl) base = atomicAdd(q == 0 ? countOut : t.escapeCount, incl);
+            base = __shfl_sync(full, base, 31);
+            sCount[q][lane] = base + incl - v;
+          }
         }
-        uint32_t base = 0;
-        if (lane == 7 && incl) base = atomicAdd(countOut, incl);
-        if (lane == 15 && incl) base = atomicAdd(t.escapeCount, incl);
-        base = __shfl_sync(full, base, (lane & 8) | 7, 32);
-        if (lane < 16) sCount[q][w] = base + incl - v;
       }
       __syncthreads();
       if (survive) {
@@ -465,6 +498,37 @@ __global__ void __launch_bounds__(kShadeThreads, kShadeBlocksPerSM) wf_shade_ker
     }
   }
   flush_counters(t.counters, 0u, 0u, Counters{0u, 0u}, nSamples, nEscaped);
+}
+
+template <bool kNif, bool kFirst>
+__global__ void __launch_bounds__(kShadeThreads, kShadeBlocksPerSM) wf_shade_kernel(const WfArgs a) {
+  __shared__ uint32_t sCountBuf[2][2][8];
+  wf_shade_body<kNif, kFirst, kShadeWarps>(a, a.qIn, sCountBuf);
+}
+
+// wf_tail: the bounces from `bounceBegin` on in ONE cooperative launch (persistent 1024-thread CTAs, one per SM, the pair
+// table staged once): trace phase, grid barrier, shade phase, grid barrier, until no path is left or bounceEnd is
+// reached. In a render with Russian roulette the paths still alive a bounce or two after roulette starts are a fraction
+// of a per cent of the chunk (bench scene: 65 K of 66 M at bounce 5), and each of their bounces otherwise costs two
+// launches, a staging of the table and a pipeline drain. Same bodies, same arithmetic, same queues: results are those
+// of the per-bounce launches (tests/test_gpu_parity.py runs both). The grid barrier orders the phases' global-memory
+// traffic (cooperative groups' grid.sync() is a release / acquire at gpu scope), and the path records are never read
+// through the non-coherent path.
+template <bool kShared, bool kCount, bool kNif>
+__global__ void __launch_bounds__(1024) wf_tail_kernel(const WfArgs a, const uint32_t bounceBegin, const uint32_t bounceEnd) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ uint32_t sCountBuf[2][2][32];
+  const uint4* pairs = stage_pairs<kShared>(a.t, reinterpret_cast<uint4*>(smemRaw));
+  const uint32_t pairsShared = opaque_shared_base<kShared>(smemRaw);
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  for (uint32_t b = bounceBegin; b < bounceEnd; ++b) {
+    const int qIn = (int)(b & 1u);
+    wf_trace_body<kShared, kCount, false>(a, qIn, pairs, pairsShared, nullptr);
+    grid.sync();
+    wf_shade_body<kNif, false, 32>(a, qIn, sCountBuf);
+    grid.sync();
+    if (__ldcg(a.b.counts + (qIn ^ 1)) == 0u) break;  // nobody survived this bounce (every thread reads the same value)
+  }
 }
 
 // rgb += colour_s (+ throughput_s * env_s when an environment light is loaded), s in chunk order.

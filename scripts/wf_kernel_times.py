@@ -14,7 +14,7 @@ s = HostScene.builtin('box').configure(1440, 1440, path_trace=True, samples=spp,
 rays = init_ray_stream(1440, 1440, s.fov)
 dev = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
 pristine = dev.clone()
-tr, sh = [], []
+tr, sh, tot = [], [], []
 extra = {'scene_residency': int(os.environ['WF_RESIDENCY'])} if 'WF_RESIDENCY' in os.environ else {}
 with B200Scene(s) as g:
     for r in range(reps + 2):
@@ -26,4 +26,5 @@ with B200Scene(s) as g:
         if r >= 2:
             tr.append(st["trace_kernel_ms"] / st["trace_kernel_launches"])
             sh.append(st["shade_kernel_ms"] / st["shade_kernel_launches"])
-print(f"trace ms/launch min {min(tr):.4f} median {np.median(tr):.4f} | shade min {min(sh):.4f} median {np.median(sh):.4f} | launches {st['trace_kernel_launches']}")
+            tot.append(st["kernel_ms"])
+print(f"trace ms/launch min {min(tr):.4f} median {np.median(tr):.4f} | shade min {min(sh):.4f} median {np.median(sh):.4f} | launches {st['trace_kernel_launches']} | step ms min {min(tot):.3f} median {np.median(tot):.3f}")

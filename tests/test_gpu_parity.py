@@ -137,6 +137,33 @@ def test_path_length_roulette_and_chunking(B200Scene, port, max_len, roulette, s
                 assert st[k] == cw[k], k
 
 
+@pytest.mark.parametrize("max_len,roulette,tail", [(10, 3, 1), (10, 3, 2), (10, 3, 5), (12, 0, 3), (6, 9, 4)])
+def test_tail_launch_equals_per_bounce_launches(B200Scene, port, max_len, roulette, tail):
+    """The cooperative tail launch (bounces >= tail_bounce in one kernel: trace phase, grid barrier, shade phase, ...)
+    against the oracle for starts from bounce 2 on, with roulette early, late and absent, and against tail_bounce = 1
+    (one trace + one shade launch per bounce): same bytes, same counters, fewer launches."""
+    w, h, spp = 96, 80, 6
+    s = scene.HostScene.builtin("box").configure(w, h, path_trace=True, samples=spp, seed=5, max_path_length=max_len,
+                                                 roulette_start_depth=roulette)
+    base = scene.init_ray_stream(w, h, s.fov)
+    want = base.copy()
+    cw = port.path_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got, tail_bounce=tail, samples_per_chunk=4, count_visits=1)
+        assert_streams_identical(got, want, f"tail_bounce={tail}")
+        st = g.stats()
+        for k in ("closest_hit_queries", "samples", "escaped_samples"):
+            assert st[k] == cw[k], k
+        plain = base.copy()
+        g.execute(plain, tail_bounce=1, samples_per_chunk=4, count_visits=1)
+        assert plain.tobytes() == got.tobytes()
+        st1 = g.stats()
+        assert st1["node_visits"] == st["node_visits"] and st1["prim_tests"] == st["prim_tests"]
+        if tail >= 2 and tail + 2 <= max_len:
+            assert st["kernel_launches"] < st1["kernel_launches"]
+
+
 def test_render_from_the_serialised_scene(B200Scene, port, box_scene):
     """The byte stream the reference uploads (Serialiser<16> of SceneRef) is enough to set the device scene up:
     rendering from the zero-copy desc over the blob equals rendering from the arrays it was written from."""
