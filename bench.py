@@ -288,6 +288,7 @@ def run_reference(args):
             vals.append(base)
     v = float(np.mean([b["value"] for b in vals]))
     sps = float(np.mean([b["samples_per_s"] for b in vals]))
+    shipped = as_shipped_cpu(args, scene) if (base["kind"] == "reference" and args.mode != "shadow") else None
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean([b["seconds"] for b in vals])) * 1e3,
@@ -300,7 +301,36 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if shipped is not None:
+        line["cpu_reference_as_shipped"] = shipped
     print(json.dumps(line))
+
+
+def as_shipped_cpu(args, scene, seconds=4.0):
+    """SURVEY.md 8d "(A)": the reference's CPU path-trace loop the way it ships -- one global generator, every draw inside
+    `omp critical`, camera rays regenerated serially per sample (trace.cpp:236-245) -- timed on a small bounded sample.
+    `value` of the reference arm stays the fair number (same kernels, one RNG stream per (pixel, sample), no lock)."""
+    from oracle import oracle_py
+
+    orc = oracle_py.Oracle("reference")
+    cores = os.cpu_count() or 1
+    w, h = args.width, args.height
+    rng = np.random.default_rng(1)
+
+    def run(n_rows, spp):
+        picks = np.sort(rng.choice(h, size=min(n_rows, h), replace=False))
+        sel = np.concatenate([init_ray_stream(w, h, scene.fov, window=(w, 1, 0, int(r))) for r in picks])
+        t0 = time.perf_counter()
+        cnt = orc.path_trace_as_shipped(scene, sel, spp, threads=cores)
+        return time.perf_counter() - t0, cnt
+
+    dt, cnt = run(4, 2)
+    rows = int(max(4, min(h, 4 * seconds / max(dt, 1e-6))))
+    dt, cnt = run(rows, 2)
+    q = cnt["closest_hit_queries"]
+    return {"value": q / dt / 1e6, "unit": UNIT, "cores": cores, "samples_per_s": cnt["samples"] / dt, "seconds": dt,
+            "sample": f"{rows} of the {h} rows x 2 spp = {cnt['samples']} samples, {q} BVH queries in {dt:.2f} s; global RNG in "
+                      f"omp critical(sample), serial camera-ray regeneration per sample, omp schedule(auto)"}
 
 
 # ------------------------------------------------------------------------------------------------

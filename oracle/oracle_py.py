@@ -75,6 +75,16 @@ class Oracle:
         assert rc == 0
         return self._counters(counters)
 
+    def path_trace_as_shipped(self, scene, rays, num_samples, threads=0):
+        """Reference build only: renderCPU's loop as shipped (one global generator, draws inside `omp critical`, serial
+        camera-ray regeneration per sample; trace.cpp:236-245). Not reproducible; for timing."""
+        assert self.kind == "reference"
+        fn = self.lib.ref_path_trace_as_shipped
+        fn.argtypes = [C.POINTER(capi.SceneDesc), C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
+        counters = np.zeros(8, dtype=np.uint64)
+        assert fn(C.byref(scene.desc), capi.ptr(rays), rays.size, num_samples, threads, capi.ptr(counters)) == 0
+        return self._counters(counters)
+
     def intersect(self, scene, rays, threads=0):
         out = np.zeros(rays.size, dtype=capi.HIT)
         counters = np.zeros(8, dtype=np.uint64)

@@ -23,6 +23,7 @@
 #include <math/sincos.hpp>
 
 #include <omp.h>
+#include <random>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -417,6 +418,90 @@ void ref_camera_sample(uint64_t rngSeed, uint32_t w, uint32_t h, float fov, floa
     const Vec3fa d = cameraSample(st, (float)rcs[3 * i], (float)rcs[3 * i + 1], (float)w, (float)h, tanTheta, aa);
     out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
   }
+}
+
+// renderCPU's path-trace loop AS SHIPPED (trace.cpp:236-245 around pathTrace :115-188): ONE global xoshiro::Generator,
+// camera rays regenerated serially before every sample with std::normal_distribution jitter (initPerspectiveRayStream,
+// src/app_utils.cpp:19-47), every draw of the bounce loop inside `omp critical(sample)` (trace.cpp:144-148, :161-165,
+// :176-181), `omp parallel for schedule(auto)` over the rays. The order of the draws depends on the OpenMP schedule, so
+// the image is not reproducible: this entry exists to TIME the reference's CPU path the way it ships (SURVEY.md 8d
+// "(A)"), next to ref_path_trace, which is the same kernels with one RNG stream per (pixel, sample) and no lock.
+int ref_path_trace_as_shipped(const b200rt_scene_desc* d, void* raysV, size_t n, uint32_t numSamples, int threads,
+                              uint64_t* counters) {
+  RefScene sc(*d);
+  CompactBvh bvh(sc.nodes, sc.maxDepth);
+  auto* rays = (TraceResult*)raysV;
+  const float tanTheta = fovTan(d->fov_radians);
+  xoshiro::Generator sampler(d->rng_seed);  // makePathTraceSettings, src/app_utils.cpp:237-239
+  std::normal_distribution<float> jitter{0.f, d->anti_alias_scale};
+  Counters total;
+  for (std::uint32_t s = 0; s < numSamples; ++s) {
+    for (size_t i = 0; i < n; ++i) {  // serial, like the reference
+      const float pu = rays[i].p.u + jitter(sampler), pv = rays[i].p.v + jitter(sampler);
+      rays[i].h = HitRecord(Vec3fa(0.f, 0.f, 0.f), pixelToRayDir(pv, pu, d->image_width, d->image_height, tanTheta));
+    }
+#pragma omp parallel num_threads(pickThreads(threads))
+    {
+      Counters cnt;
+      auto lookup = [&](std::uint16_t geomID, std::uint32_t) { cnt.prims += 1; return sc.prim(geomID); };
+#pragma omp for schedule(auto)
+      for (long long i = 0; i < (long long)n; ++i) {
+        TraceResult& result = rays[i];
+        auto& hit = result.h;
+        cnt.samples += 1;
+        hit.throughput = Vec3fa(1.f, 1.f, 1.f);
+        Vec3fa color(0.f, 0.f, 0.f);
+        for (std::uint32_t i2 = 0; i2 < d->max_path_length; ++i2) {
+          offsetRay(hit.r, hit.normal);
+          hit.r.tMin = 0.f;
+          hit.r.tMax = std::numeric_limits<float>::infinity();
+          cnt.closest += 1;
+          auto isect = bvh.intersect(hit.r, lookup);
+          if (isect) {
+            updateHit(isect, hit);
+            const Material& material = sc.materials[sc.matIDs[hit.geomID]];
+            if (material.emissive) { color += hit.throughput * material.emission; }
+            if (material.type == Material::Type::Diffuse) {
+              float u1, u2;
+#pragma omp critical(sample)
+              {
+                u1 = sampler.uniform_0_1();
+                u2 = sampler.uniform_0_1();
+              }
+              hit.r.direction = sampleDiffuse(hit.normal, u1, u2);
+              hit.throughput *= material.albedo;
+            } else if (material.type == Material::Type::Specular) {
+              hit.r.direction = reflect(hit.r.direction, hit.normal);
+              hit.throughput *= material.albedo;
+            } else if (material.type == Material::Type::Refractive) {
+              float u1;
+#pragma omp critical(sample)
+              { u1 = sampler.uniform_0_1(); }
+              const auto [ndir, refracted] = dielectric(hit.r, hit.normal, material.ior, u1);
+              hit.r.direction = ndir;
+              if (refracted) { hit.throughput *= material.albedo; }
+            } else {
+              result.rgb *= std::numeric_limits<float>::quiet_NaN();
+              hit.flags |= HitRecord::ERROR;
+            }
+          } else {
+            hit.flags |= HitRecord::ESCAPED;
+            cnt.escaped += 1;
+            break;
+          }
+          if (i2 > d->roulette_start_depth) {
+            float u1;
+#pragma omp critical(sample)
+            { u1 = sampler.uniform_0_1(); }
+            if (evaluateRoulette(u1, hit.throughput)) { break; }
+          }
+        }
+        result.rgb += color;
+      }
+      cnt.flush(counters);
+    }
+  }
+  return 0;
 }
 
 int ref_nif_eval(const b200rt_nif_desc*, const float*, size_t, float*, int) { return -4; /* no CPU NIF in the reference */ }
