@@ -50,8 +50,8 @@ for l in launch.values():
 total = sum(a["ms"] for a in agg.values())
 shutil.copy(src / f"{tag}_launches.csv", out / f"{tag}_launches.csv")
 with open(out / f"{tag}_launches_summary.txt", "w") as f:
-    f.write(f"# ncu launch list of `python bench.py --steps 1 --warmup 0 --samples {int(spp_list)} --skip-cpu-baseline` ({len(launch)} launches = "
-            f"{int(spp_list) // 32} chunks of 32 spp), --clock-control none; per-launch times under ncu are serialised and cold-cache:\n"
+    f.write(f"# ncu launch list of `python bench.py --steps 1 --warmup 0 --samples {int(spp_list)} --skip-cpu-baseline` ({len(launch)} launches captured: bounce-0 to bounce-4 "
+            f"trace / shade pairs, the tail launch, NIF and accumulate of each 32-spp chunk), --clock-control none; per-launch times under ncu are serialised and cold-cache:\n"
             f"# the SHARES are what must agree with bench.py's event timing, not the absolute times.\n"
             f"# kernel, launches, total ms, share, avg ms, DRAM read GB, DRAM write GB, lanes per instruction (time-weighted), issue-active % (time-weighted)\n")
     for k, a in agg.items():
@@ -73,7 +73,7 @@ for l in launch.values():
             chunks.append(cur_chunk)
             cur_chunk = None
 chunks_per_step = spp_step / 32.0
-group = {"wf_trace_kernel": "wf_trace", "wf_shade_kernel": "wf_shade", "nif_mlp_kernel": "nif_mlp", "wf_accumulate_kernel": "wf_accumulate"}
+group = {"wf_trace_kernel": "wf_trace", "wf_shade_kernel": "wf_shade", "wf_tail_kernel": "wf_tail", "nif_mlp_kernel": "nif_mlp", "wf_accumulate_kernel": "wf_accumulate"}
 traffic = {}
 for name, pat in group.items():
     per_chunk = [sum(l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0) for l in c if pat in l["kernel"]) for c in chunks]
