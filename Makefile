@@ -47,6 +47,13 @@ tests/libhostpair.so: tests/host_pair_check.cpp $(CSRC)/rt_prims.h $(CSRC)/pair_
                       $(CSRC)/sin_deg_table.inc include/b200rt.h
 	$(CXX) $(HOSTFLAGS) -I/usr/local/cuda/include -shared -o $@ $<
 
+# measured-slower kernel variants, never part of the product library (scripts/experiments/README.md):
+#   variants/libb200rt_pair.so = the CTA-pair NIF kernel (csrc/nif_tc_pair2.cuh), run with B200RT_LIB=... B200RT_NIF_PAIR=2
+experiments: $(CSRC)/b200rt.o
+	mkdir -p $(PKG)/variants
+	$(NVCC) $(NVFLAGS_NIF) -DB200RT_NIF_PAIR_KERNEL -c -o $(PKG)/variants/nif_pair.o $(CSRC)/nif.cu
+	$(NVCC) $(ARCH) -shared -ccbin $(CXX) -o $(PKG)/variants/libb200rt_pair.so $(CSRC)/b200rt.o $(PKG)/variants/nif_pair.o -cudart static
+
 sass: $(PKG)/libb200rt.so
 	/usr/local/cuda/bin/cuobjdump -sass $(PKG)/libb200rt.so > /tmp/b200rt.sass
 
@@ -54,4 +61,4 @@ clean:
 	rm -f $(CSRC)/*.o $(PKG)/*.so $(PKG)/trace
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean sass
+.PHONY: all oracle clean sass experiments

@@ -23,7 +23,11 @@
 #include <string>
 #include <vector>
 
+#ifdef B200RT_NIF_PAIR_KERNEL
+#include "nif_tc_pair2.cuh"  // experiment build: the CTA-pair kernel, selected with B200RT_NIF_PAIR=2
+#else
 #include "nif_tc.cuh"
+#endif
 
 namespace rt {
 
@@ -61,6 +65,12 @@ struct NifModel {
   tc::Params tc{};
   size_t tcSmem = 0;
   std::string tcWhyNot;
+#ifdef B200RT_NIF_PAIR_KERNEL
+  tc::Params tc2{};   // tiling of the CTA-pair kernel (nif_tc_pair2.cuh): 128 / 192 column split
+  tc2::PairMaps maps{};
+  bool tc2Ok = false;
+  size_t pair2Smem = 0;
+#endif
 };
 
 namespace {
@@ -170,6 +180,118 @@ bool prepare_tc(NifModel* m, const b200rt_nif_desc& d) {
   return true;
 }
 
+#ifdef B200RT_NIF_PAIR_KERNEL
+// Same for the CTA-pair kernel (nif_tc_pair2.cuh): N0 = 128 / N1 = 192 columns, K_lo = the previous layer's first 128
+// outputs (+ ones slice + encoded input), and only the per-rank half images (columns [r n/2, (r+1) n/2) of every block).
+// Requires hidden width 320. All layers' images go into one buffer that the kernel reads through TMA tensor maps over
+// its 128-byte rows (one map per stage height).
+bool prepare_tc2(NifModel* m, const b200rt_nif_desc& d) {
+  const int E = (int)d.embedding_dimension, F = 4 * E;
+  if (F % 16 != 0 || 2 + F / 8 > tc2::kStaticPlanesMax || (int)d.num_layers > tc::kMaxLayers) return false;
+  tc::Params& t = m->tc2;
+  t = tc::Params{};
+  t.numLayers = (int)d.num_layers;
+  t.embed = E;
+  int width = F, prevN0 = 0;
+  std::vector<int> actRows(d.num_layers), featRows(d.num_layers);
+  for (uint32_t i = 0; i < d.num_layers; ++i) {
+    const b200rt_nif_layer& L = d.layers[i];
+    tc::Layer& o = t.layers[i];
+    const int K = (int)L.in_features;
+    o.N = (int)L.out_features; o.Npad = (o.N + 15) / 16 * 16; o.relu = L.relu;
+    const bool last = i + 1 == d.num_layers;
+    if (!last && o.N != tc2::kN0 + tc2::kN1) return false;
+    if (last && o.Npad > 16) return false;
+    o.n0 = std::min(o.Npad, tc2::kN0);
+    o.n1 = o.Npad - o.n0;
+    if (i == 0) { if (K != F) return false; actRows[i] = 0; featRows[i] = F; }
+    else if (K == width + F) { actRows[i] = width; featRows[i] = F; }
+    else if (K == width) { actRows[i] = width; featRows[i] = 0; }
+    else return false;
+    o.actLoSlices = std::min(actRows[i], prevN0) / 16;
+    o.actHiSlices = actRows[i] / 16 - o.actLoSlices;
+    o.staticSlices = 1 + featRows[i] / 16;
+    width = o.N;
+    prevN0 = o.n0;
+  }
+  if (width != 3) return false;
+  t.maxv = d.max; t.mean0 = d.mean[0]; t.mean1 = d.mean[1]; t.mean2 = d.mean[2];
+  t.logToneMap = d.log_tone_map;
+  m->pair2Smem = (size_t)(tc2::kActPlanes + tc2::kStaticPlanesMax) * tc2::kPlaneBytes + (size_t)tc2::kStages * tc2::kStageBytes +
+                 (2 * tc2::kStages + 6) * 8 + 16;
+  int maxSmem = 0;
+  cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
+  if (m->pair2Smem > (size_t)maxSmem) return false;
+  std::vector<__half> all;
+  for (uint32_t i = 0; i < d.num_layers; ++i) {
+    const b200rt_nif_layer& L = d.layers[i];
+    tc::Layer& o = t.layers[i];
+    const __half* src = reinterpret_cast<const __half*>(L.kernel_f16);
+    const __half* bias = reinterpret_cast<const __half*>(L.bias_f16);
+    const int loAct = 16 * o.actLoSlices, hiAct = 16 * o.actHiSlices;
+    const int loK = loAct + 16 * o.staticSlices;
+    std::vector<__half> img;
+    auto block = [&](int kRows, int nBase, int nCols, auto&& value) {
+      const size_t at = img.size();
+      img.resize(at + (size_t)kRows * nCols, __float2half(0.f));
+      for (int k = 0; k < kRows; ++k)
+        for (int n = 0; n < nCols; ++n)
+          if (nBase + n < o.N) img[at + ((size_t)(k / 8) * nCols + n) * 8 + (k % 8)] = value(k, nBase + n);
+    };
+    auto loValue = [&](int k, int n) -> __half {
+      if (k < loAct) return src[(size_t)k * o.N + n];
+      if (k == loAct) return bias ? bias[n] : __float2half(0.f);
+      if (k < loAct + 16) return __float2half(0.f);
+      return src[(size_t)(actRows[i] + (k - loAct - 16)) * o.N + n];
+    };
+    auto hiValue = [&](int k, int n) -> __half { return src[(size_t)(loAct + k) * o.N + n]; };
+    o.pairRow0 = (uint32_t)(all.size() * 2 / 128);
+    for (int r = 0; r < 2; ++r) {
+      img.clear();
+      block(loK, r * (o.n0 / 2), o.n0 / 2, loValue);
+      if (o.n1) block(loK, o.n0 + r * (o.n1 / 2), o.n1 / 2, loValue);
+      if (hiAct) block(hiAct, r * (o.n0 / 2), o.n0 / 2, hiValue);
+      if (hiAct && o.n1) block(hiAct, o.n0 + r * (o.n1 / 2), o.n1 / 2, hiValue);
+      if ((img.size() * 2) % 128 != 0) return false;
+      if (r == 0) o.pairRankRows = (uint32_t)(img.size() * 2 / 128);
+      all.insert(all.end(), img.begin(), img.end());
+    }
+    o.wimg = nullptr;
+  }
+  // slack rows behind the last image: a box never reaches past the tensor
+  const size_t rows = all.size() * 2 / 128;
+  void* dp = nullptr;
+  if (cudaMalloc(&dp, (rows + 72) * 128) != cudaSuccess) return false;
+  m->allocs.push_back(dp);
+  cudaMemset(dp, 0, (rows + 72) * 128);
+  cudaMemcpy(dp, all.data(), all.size() * 2, cudaMemcpyHostToDevice);
+  // tensor maps (driver entry point fetched through the runtime: no libcuda link)
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) { cudaGetLastError(); return false; }
+  const uint32_t planeClass[3] = {128u, 1024u, 1536u};
+  for (int c = 0; c < 3; ++c)
+    for (int np = 2; np <= 6; np += 2) {
+      const cuuint64_t gdim[2] = {32, (cuuint64_t)(rows + 72)};
+      const cuuint64_t gstride[1] = {128};
+      const cuuint32_t box[2] = {32, (cuuint32_t)(np * planeClass[c] / 128)};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult rc = ((EncodeFn)fn)(&m->maps.m[tc2::pair_map_index(planeClass[c], (uint32_t)np)], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, dp,
+                                         gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc != CUDA_SUCCESS) { std::fprintf(stderr, "[nif pair] cuTensorMapEncodeTiled failed: %d (class %d planes %d)\n", (int)rc, c, np); return false; }
+    }
+  if (cudaFuncSetAttribute(tc2::nif_mlp_tc_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->pair2Smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+#endif
+
 }  // namespace
 
 const char* nif_last_error() { return g_nifError.c_str(); }
@@ -230,6 +352,9 @@ NifModel* nif_create(const b200rt_nif_desc& d, int device) {
   // Tensor-core path (the product path). Models outside its tiling rules (widths not multiples of 16)
   // run on the CUDA-core kernel below; B200RT_NIF_IMPL=simt forces that kernel for debugging.
   m->tcOk = prepare_tc(m, d);
+#ifdef B200RT_NIF_PAIR_KERNEL
+  m->tc2Ok = m->tcOk && prepare_tc2(m, d);
+#endif
   const char* impl = std::getenv("B200RT_NIF_IMPL");
   if (impl && std::strcmp(impl, "simt") == 0) { m->tcOk = false; m->tcWhyNot = "forced by B200RT_NIF_IMPL=simt"; }
   // Weight uploads came from pageable memory on the default stream; the kernels run on the caller's non-blocking
@@ -349,8 +474,32 @@ static int launch(NifModel* m, const float* uvDirect, const float* slotEscape, c
       cudaMemsetAsync(dProf, 0, (size_t)tcGrid * 16 * sizeof(unsigned long long), stream);
       params.prof = dProf;
     }
-    tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(params, uvDirect, slotEscape, queue, dCount, count, first, out);
-    const cudaError_t te = cudaGetLastError();
+    cudaError_t te;
+#ifdef B200RT_NIF_PAIR_KERNEL
+    static const int pairMode = [] { const char* e = std::getenv("B200RT_NIF_PAIR"); return e ? std::atoi(e) : 0; }();
+    if (pairMode == 2 && m->tc2Ok && sms >= 2) {  // CTA-pair kernel (nif_tc_pair2.cuh)
+      tc::Params params2 = m->tc2;
+      params2.prof = params.prof;
+      const uint32_t groups = (tcTiles + 1u) / 2u;
+      const uint32_t maxPairs = maxGrid / 2u;
+      const uint32_t pairs = groups < maxPairs ? (groups ? groups : 1u) : maxPairs;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2u * pairs);
+      cfg.blockDim = dim3(tc2::kThreads);
+      cfg.dynamicSmemBytes = m->pair2Smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      te = cudaLaunchKernelEx(&cfg, tc2::nif_mlp_tc_pair2_kernel, params2, m->maps, uvDirect, slotEscape, queue, dCount, count, first, out);
+    } else
+#endif
+    {
+      tc::nif_mlp_tc_kernel<<<tcGrid, tc::kThreads, m->tcSmem, stream>>>(params, uvDirect, slotEscape, queue, dCount, count, first, out);
+      te = cudaGetLastError();
+    }
     if (te != cudaSuccess) { g_nifError = cudaGetErrorString(te); return -1; }
     if (profile) {  // debugging aid: per-role cycle breakdown of CTA 0 (synchronises!)
       std::vector<unsigned long long> h((size_t)tcGrid * 16);

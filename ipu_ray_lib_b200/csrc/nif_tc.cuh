@@ -61,6 +61,7 @@ struct Layer {
   int N, Npad;          // Npad = N rounded up to 16, <= 320
   int n0, n1;           // columns of the two halves: n0 = min(Npad, 160), n1 = Npad - n0
   int relu;
+  uint32_t pairRow0, pairRankRows;  // experiment build (nif_tc_pair2.cuh): the layer's per-rank images in the 128-B-row view
 };
 
 struct Params {

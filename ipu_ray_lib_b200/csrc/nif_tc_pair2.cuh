@@ -5,9 +5,12 @@
 //   * lo columns of the A operand double-buffered by layer parity: N0 is drained into the buffer the NEXT layer reads
 //     and that layer's first blocks are released while block B3 of the current layer still runs,
 //   * Fourier features of the next tile encoded by dedicated warps.
-// The hand-offs that cross the pair (epilogue warps of both CTAs -> leader's activation barriers, peer's weight
-// arrivals -> leader, leader's commits -> both CTAs) cost a DSMEM round trip each; here they are all early.
-// Shares the PTX wrappers of nif_tc.cuh / nif_tc_pair.cuh; has its own tiling constants and weight images (tc2::).
+// The hand-offs that cross the pair: epilogue warps of both CTAs -> leader's activation barriers (remote arrive),
+// leader's commits -> both CTAs (multicast), and the weight arrivals: BOTH producers load their half of a ring stage
+// with a TMA tensor copy that counts its bytes on the LEADER's barrier (cp.async.bulk.tensor .cta_group::2), so the
+// leader waits on one local barrier per stage and nothing is relayed.
+// EXPERIMENT BUILD ONLY (-DB200RT_NIF_PAIR_KERNEL). Shares the PTX wrappers of nif_tc.cuh / nif_tc_pair.cuh; has its
+// own tiling constants and weight images (tc2::).
 #pragma once
 #include "nif_tc_pair.cuh"
 
@@ -71,18 +74,27 @@ __device__ __forceinline__ void drain_to_x(uint32_t taddr, bool relu, unsigned c
 }
 static_assert(kN0 == 128 && kN1 == 192, "the epilogue splits N0 into 2 x 64 and N1 into 2 x (64 + 32) columns");
 
+// The pair images of all layers live in ONE buffer viewed as rows of 128 B; a ring stage is `planes` (2, 4 or 6) planes of
+// planeBytes (128 B: output layer, 1024 B: N0 halves, 1536 B: N1 halves) = a box of planes x planeBytes / 128 rows. One
+// tensor map per box height, indexed [plane size class][planes / 2 - 1].
+struct PairMaps {
+  CUtensorMap m[9];
+};
+__host__ __device__ inline int pair_map_index(uint32_t planeBytes, uint32_t planes) {
+  return (planeBytes == 128u ? 0 : (planeBytes == 1024u ? 1 : 2)) * 3 + (int)(planes / 2u) - 1;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-nif_mlp_tc_pair2_kernel(const Params p, const float* __restrict__ uvDirect, const float* __restrict__ slotEscape,
-                  const uint32_t* __restrict__ queue, const uint32_t* __restrict__ dCount, uint32_t directCount,
-                  float* __restrict__ out) {
+nif_mlp_tc_pair2_kernel(const Params p, const __grid_constant__ PairMaps maps, const float* __restrict__ uvDirect,
+                  const float* __restrict__ slotEscape, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ dCount,
+                  uint32_t directCount, uint32_t first, float* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // layout: [activation planes: lo x 2, hi][static planes: ones, encoded input][ring stages][barriers][tmem ptr]
   unsigned char* X = smem;                                   // [lo buffer 0][lo buffer 1][hi]
   unsigned char* S = X + (size_t)kActPlanes * kPlaneBytes;
   unsigned char* ring = S + (size_t)kStaticPlanesMax * kPlaneBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * kStageBytes);
-  uint64_t* peerFull = bars + 2 * kStages + 6;  // [kStages] (leader) the peer's half of the stage has landed
-  uint64_t* fullBar = bars;                    // [kStages] weights landed
+  uint64_t* fullBar = bars;                    // [kStages] (leader's) BOTH halves of the stage have landed
   uint64_t* emptyBar = bars + kStages;         // [kStages] MMAs that read the stage have completed
   uint64_t* actLoBar = bars + 2 * kStages;     // lo columns (+ features) of the next A operand are in place (256 arrivals)
   uint64_t* actHiBar = bars + 2 * kStages + 1; // hi columns are in place (256 arrivals)
@@ -90,13 +102,13 @@ nif_mlp_tc_pair2_kernel(const Params p, const float* __restrict__ uvDirect, cons
   uint64_t* accBar1 = bars + 2 * kStages + 3;  // N1 accumulator complete == every MMA of the layer complete (commit)
   uint64_t* featFreeBar = bars + 2 * kStages + 4;   // the feature planes may be overwritten (256 epilogue arrivals per tile)
   uint64_t* featReadyBar = bars + 2 * kStages + 5;  // the next tile's features are in place (256 encoder arrivals per tile)
-  uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 6);
+  uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
 
   // warp index made provably warp-uniform (shuffle from lane 0), so the role branches below are uniform branches and
   // the issuer's descriptors live in uniform registers instead of being re-broadcast per MMA
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t count = uvDirect ? directCount : min(*dCount, directCount);
+  const uint32_t count = uvDirect ? directCount : min(*dCount > first ? *dCount - first : 0u, directCount);
   const uint32_t numTiles = (count + kRows - 1) / kRows;
   // CTA pair: rank 0 (leader) issues the MMAs for both; pair q works on tiles 2g + rank, g = q, q + numPairs, ...
   const uint32_t crank = cluster_ctarank();
@@ -106,7 +118,7 @@ nif_mlp_tc_pair2_kernel(const Params p, const float* __restrict__ uvDirect, cons
   const uint32_t featReadyRemote = mapa_u32(smem_u32(featReadyBar), 0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(fullBar + s, 1); mbar_init(emptyBar + s, 1); mbar_init(peerFull + s, 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(fullBar + s, 1); mbar_init(emptyBar + s, 1); }
     mbar_init(actLoBar, 2 * kEpiWarps);  // one arrive per epilogue warp of BOTH CTAs, on the leader's barrier
     mbar_init(actHiBar, 2 * kEpiWarps);
     mbar_init(accBar0, 1);
@@ -136,7 +148,8 @@ nif_mlp_tc_pair2_kernel(const Params p, const float* __restrict__ uvDirect, cons
       for (uint32_t g = pairId; g < numGroups; g += numPairs) {
         for (int l = 0; l < p.numLayers; ++l) {
           const Layer& L = p.layers[l];
-          const unsigned char* src = reinterpret_cast<const unsigned char*>(L.wimgPair) + (size_t)crank * L.pairRankBytes;
+          // this CTA's image of the layer starts at row pairRow0 + rank * pairRankRows of the 128-byte-row view
+          uint32_t row = L.pairRow0 + crank * L.pairRankRows;
           const uint32_t loPlanes = 2u * (uint32_t)(L.actLoSlices + L.staticSlices), hiPlanes = 2u * (uint32_t)L.actHiSlices;
 #pragma unroll 1
           for (int b = 0; b < 4; ++b) {
@@ -144,13 +157,16 @@ nif_mlp_tc_pair2_kernel(const Params p, const float* __restrict__ uvDirect, cons
             const uint32_t planeBytes = (uint32_t)((b & 1) ? L.n1 : L.n0) * 8u;  // n/2 columns x 16 B
             if (planeBytes == 0u) continue;
             for (uint32_t pl = 0; pl < planes; pl += kStageK / 8) {
-              const uint32_t bytes = min((uint32_t)(kStageK / 8), planes - pl) * planeBytes;
+              const uint32_t np = min((uint32_t)(kStageK / 8), planes - pl);
+              const uint32_t bytes = np * planeBytes;
               { NIF_PROF_T0(); mbar_wait(emptyBar + stage, phase ^ 1u); NIF_PROF_ADD(waitEmpty); }
-              mbar_expect_tx(fullBar + stage, bytes);
-              bulk_load(ring + (size_t)stage * kStageBytes, src + (size_t)pl * planeBytes, bytes, fullBar + stage);
+              // the leader's barrier counts the bytes of both halves; the peer's copy signals it directly
+              if (crank == 0) mbar_expect_tx(fullBar + stage, 2u * bytes);
+              tma_load_2d_pair(ring + (size_t)stage * kStageBytes, &maps.m[pair_map_index(planeBytes, np)], 0,
+                               (int)(row + pl * (planeBytes >> 7)), fullBar + stage);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
-            src += (size_t)planes * planeBytes;
+            row += planes * (planeBytes >> 7);
           }
         }
       }
@@ -192,30 +208,8 @@ nif_mlp_tc_pair2_kernel(const Params p, const float* __restrict__ uvDirect, cons
     }
     if (p.prof && w == 0 && lane == 0) p.prof[(size_t)blockIdx.x * 16 + PF_EPI_ENCODE] = encodeCyc;
   } else if (warp > kEpiWarps) {
-    // ===== MMA issuer (leader CTA) / weight-arrival relay (peer CTA) =====
-    if (crank != 0) {
-      // The leader's MMAs read this CTA's half of B as well: tell it when each of our ring stages has landed. A remote
-      // arrive is a ~500-cycle round trip, so lane s owns ring stage s and the notifications overlap.
-      uint32_t stagesPerTile = 0;
-      for (int l = 0; l < p.numLayers; ++l) {
-        const Layer& L = p.layers[l];
-        const uint32_t loPlanes = 2u * (uint32_t)(L.actLoSlices + L.staticSlices), hiPlanes = 2u * (uint32_t)L.actHiSlices;
-        const uint32_t perLo = (loPlanes + kStageK / 8 - 1) / (kStageK / 8), perHi = (hiPlanes + kStageK / 8 - 1) / (kStageK / 8);
-        stagesPerTile += (perLo + perHi) * ((L.n0 ? 1u : 0u) + (L.n1 ? 1u : 0u));
-      }
-      uint32_t groupsMine = 0;
-      for (uint32_t g = pairId; g < numGroups; g += numPairs) groupsMine++;
-      const uint32_t total = groupsMine * stagesPerTile;
-      if (lane < kStages) {
-        const uint32_t remote = mapa_u32(smem_u32(peerFull + lane), 0);
-        uint32_t phase = 0;
-        for (uint32_t i = (uint32_t)lane; i < total; i += kStages) {
-          mbar_wait(fullBar + lane, phase);
-          mbar_arrive_remote(remote);
-          phase ^= 1u;
-        }
-      }
-    } else {
+    // ===== MMA issuer (leader CTA; the peer's warp idles) =====
+    if (crank == 0) {
     // The issuing thread is a scalar instruction stream on the critical path of the tensor pipe (one MMA must be
     // issued every <= 80 cycles), so the K loop is kept to a handful of 32-bit adds per MMA: only the low word of a
     // descriptor (start address) changes, everything else is hoisted per block.
@@ -241,7 +235,7 @@ nif_mlp_tc_pair2_kernel(const Params p, const float* __restrict__ uvDirect, cons
       uint32_t aLo = switchAt ? aStart : aLoS;
       uint32_t ks = 0;
       while (ks < slices) {
-        { const long long w0 = p.prof ? clock64() : 0; mbar_wait(fullBar + stage, phase); mbar_wait(peerFull + stage, phase); if (p.prof) waitFull += (unsigned long long)(clock64() - w0); }
+        { const long long w0 = p.prof ? clock64() : 0; mbar_wait(fullBar + stage, phase); if (p.prof) waitFull += (unsigned long long)(clock64() - w0); }
         tc_fence_after();
         uint32_t bLo = bLoBase + stage * stageStep;
 #pragma unroll
