@@ -260,11 +260,12 @@ int main(int argc, char** argv) {
     std::snprintf(label, sizeof label, "policy 0 (kernel), thr %d", thr);
     report(label, simulate(v.dev, rays, c, 0, thr, 0, 0));
   }
+  const double extra = std::getenv("SIM_EXTRA") ? std::atof(std::getenv("SIM_EXTRA")) : 12.0;  // slots per iteration for routing contexts
   for (int K : {2, 3, 4})
-    for (int thr : {16, 24, 28}) {
+    for (int thr : {12, 16, 24, 28}) {
       char label[64];
-      std::snprintf(label, sizeof label, "%d queries per lane, thr %d (+12)", K, thr);
-      report(label, simulate_multi(v.dev, rays, c, thr, K, 12));
+      std::snprintf(label, sizeof label, "%d queries per lane, thr %d (+%.0f)", K, thr, extra);
+      report(label, simulate_multi(v.dev, rays, c, thr, K, extra));
     }
   report("policy 1 (lanes per slot)", simulate(v.dev, rays, c, 1, 0, 0, 0));
   for (int lt : {4, 8, 12, 16})
