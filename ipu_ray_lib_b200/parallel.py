@@ -44,15 +44,19 @@ def gather_stream(local: np.ndarray, num_rays: int, rays_per_batch: int, dist=No
     world, rank = dist.get_world_size(), dist.get_rank()
     counts = [int(batch_owner_mask(num_rays, rays_per_batch, world, r).sum()) for r in range(world)]
     item = local.dtype.itemsize
-    mine = torch.from_numpy(local.view(np.uint8).reshape(-1).copy())
+    # shards differ by up to one ray batch and NCCL's gather wants equal sizes: every rank sends max(shard) bytes (its
+    # own rays, zero-padded) and `dst` keeps the first counts[r] rays of rank r's buffer
+    size = max(counts) * item
+    mine = torch.zeros(size, dtype=torch.uint8)
+    mine[:local.size * item] = torch.from_numpy(local.view(np.uint8).reshape(-1).copy())
     use_cuda = dist.get_backend() == "nccl"
     if use_cuda:
         mine = mine.cuda()
     bufs = None
     if rank == dst:
-        bufs = [torch.empty(c * item, dtype=torch.uint8, device=mine.device) for c in counts]
+        bufs = [torch.empty(size, dtype=torch.uint8, device=mine.device) for _ in counts]
     dist.gather(mine, bufs, dst=dst)
     if rank != dst:
         return None
-    shards = [b.cpu().numpy().view(local.dtype) for b in bufs]
+    shards = [b.cpu().numpy()[:c * item].view(local.dtype) for b, c in zip(bufs, counts)]
     return merge_shards(shards, num_rays, rays_per_batch)
