@@ -267,6 +267,31 @@ def test_full_size_config2_path_trace_window(B200Scene, port):
         assert_streams_identical(split, want, "10 + 6 samples")
 
 
+def test_full_frame_config2_and_config4_bit_exact(B200Scene, port):
+    """Whole frames at the sizes BASELINE.json names, few samples: every one of the 2 073 600 paths-per-sample of
+    config 2 (1440 x 1440, path trace, seed 1442, 3 spp, no environment light) and every ray of the 3840 x 2160
+    shadow-trace frame (config 4's size) against the oracle, byte for byte, through the host-streaming entry point."""
+    s = scene.HostScene.builtin("box").configure(1440, 1440, path_trace=True, samples=3, seed=1442)
+    base = scene.init_ray_stream(1440, 1440, s.fov)
+    want = base.copy()
+    cw = port.path_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got)
+        st = g.stats()
+    assert_streams_identical(got, want, "config 2 full frame, 3 spp")
+    assert st["closest_hit_queries"] == cw["closest_hit_queries"] and st["escaped_samples"] == cw["escaped_samples"]
+    del got, want
+    s.configure(3840, 2160, path_trace=False)
+    base = scene.init_ray_stream(3840, 2160, s.fov)
+    want = base.copy()
+    port.shadow_trace(s, want)
+    with B200Scene(s) as g:
+        got = base.copy()
+        g.execute(got)
+    assert_streams_identical(got, want, "3840 x 2160 shadow trace")
+
+
 def test_random_and_degenerate_queries(B200Scene, port, box_scene, spheres_scene):
     rng = np.random.default_rng(11)
     for s, lo, hi in ((box_scene, (-300, -300, -1400), (300, 300, -700)), (spheres_scene, (-4, -2, -8), (4, 3, 0))):
