@@ -26,12 +26,13 @@
 // In-place update stays safe (nothing is stored into X before all MMAs of the layer have completed), and no MMA
 // ever targets a TMEM slot that is still being drained (the third slot).
 // Measured limits (B200): every CTA re-streams the 1.16 MB of weights per 128-row tile, 28.4 K cycles per tile =
-// 41 B/cycle/SM against ~42.6 B/cycle/SM of L2 -> SM read rate (6300 B/cycle chip-wide over 148 SMs). The cap is per
-// SM: with 74 ... 148 CTAs (B200RT_NIF_GRID) the cycles per tile do not move (profiles/r02_nif_grid.txt). TMEM drains
-// at 64 B/cycle/SM (2560 cycles per layer against 3360 cycles of MMAs). Variants that hide the epilogue completely
-// (128/192 column split, double-buffered lo columns, feature encode on dedicated warps; kept under
-// scripts/experiments/) remove the layer-boundary bubbles but then wait for weights instead: 28 K cycles per tile
-// either way. The next step is structural (fewer weight bytes per row): cta_group::2 CTA pairs, each SM loading half of B.
+// 41 B/cycle/SM (0.96 of 6300 B/cycle chip-wide over 148 SMs). The cycles per tile do not move with 74 ... 148 CTAs
+// (B200RT_NIF_GRID, profiles/r02_nif_grid.txt) nor with 2.7 % fewer weight bytes: they are ~17 K of MMA issue + 7.4 K at
+// the layer hand-offs (TMEM drains at 64 B/cycle/SM: 2560 cycles per layer against 3360 cycles of MMAs, activations
+// updated in place) + 2.6-3.8 K of ring refill latency (a bulk copy has ~200-250 cycles of fixed cost: stages below
+// 20 KB starve the ring). Variants that hide the epilogue completely (128/192 column split, double-buffered lo columns,
+// feature encode on dedicated warps) pay with a shallower ring and end at the same 28 K; the cta_group::2 CTA pair
+// (nif_tc_pair2.cuh, experiment build) halves the stream but lengthens every hand-off. scripts/experiments/README.md.
 // Roles: warps 0-7 = encode + epilogue, warp 8 lane 0 = weight producer, warp 9 = MMA issuer (whole warp converged,
 // one elected lane issues, so descriptors stay in uniform registers).
 #pragma once
