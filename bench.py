@@ -493,6 +493,15 @@ def run_b200(args):
         if shadow and args.steps > ring_n:
             line["config"]["l2_policy"] += f"; steps beyond {ring_n} refresh their copy inside the timed region"
         line.update(rooflines(prof, peaks, n_local, spp, flops_per_lookup, line["clocks"].get("sm_mhz"), shadow, nif_tile_bytes))
+        if nif is not None and not shadow:
+            line["chunk_overlap"] = {
+                "timed_steps": "library default (on): NIF + accumulate of chunk c on a second stream beside the trace / shade "
+                               "kernels of chunk c + 1; bit-identical frame",
+                "ms_per_step": dev_ms / args.steps,
+                "roofline_step": "one extra untimed step with chunk_overlap off (kernels serialised): per-kernel event "
+                                 "spans, shares and roofline fractions are the kernels' own",
+                "ms_serialised_step": prof["kernel_ms"],
+            }
         if not args.skip_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args, scene, nif, kind_pref=("port",), seconds=args.cpu_seconds)
         elif world > 1:
@@ -509,9 +518,12 @@ def kernel_breakdown(g, work, pristine, n_local, stream, params, shadow):
     import torch
 
     out = {}
-    # one more full step: the library brackets every kernel launch with CUDA events on the launching stream
+    # one more full step: the library brackets every kernel launch with CUDA events on the launching stream. This step
+    # runs with chunk_overlap off: in the timed steps (library default) the NIF kernel of chunk c shares the SMs with
+    # the trace / shade kernels of chunk c + 1, so a kernel's event span there is not the kernel's own time. Serialised,
+    # the spans add up to the step and agree with the ncu launch list (which serialises kernels too).
     work.copy_(pristine)
-    g.execute_device(work.data_ptr(), n_local, stream=stream, **params)
+    g.execute_device(work.data_ptr(), n_local, stream=stream, **dict(params, chunk_overlap=1))
     st = g.stats()
     for k in ("kernel_ms", "trace_kernel_ms", "nif_kernel_ms", "accumulate_kernel_ms", "shade_kernel_ms", "kernel_launches",
               "trace_kernel_launches", "nif_kernel_launches", "shade_kernel_launches", "escaped_samples", "samples"):

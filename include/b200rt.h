@@ -111,7 +111,10 @@ typedef struct b200rt_trace_params {
                                 * of two launches per bounce. 0 = auto (roulette_start_depth + 2: with Russian roulette the
                                 * paths still alive by then are a fraction of a per cent of a chunk), 1 = never (one trace
                                 * and one shade launch per bounce), N >= 2 = from bounce N. Same results either way */
-  uint32_t reserved[1];
+  uint32_t chunk_overlap;      /* NIF-lit wavefront renders of more than one chunk: 0 = auto, 1 = off, 2 = on. On: the NIF MLP
+                                * and the accumulate of chunk c run on a second CUDA stream while chunk c + 1 is traced
+                                * and shaded (two sets of per-sample records); accumulates stay in chunk order, results
+                                * are bit-identical */
 } b200rt_trace_params;
 
 /* Counters of the last trace (device-side counted, exact). */

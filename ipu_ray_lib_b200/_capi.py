@@ -78,7 +78,7 @@ class TraceParams(C.Structure):
         ("rays_per_batch", C.c_uint32), ("traversal", C.c_uint32),
         ("scene_residency", C.c_uint32), ("samples_per_chunk", C.c_uint32),
         ("count_visits", C.c_uint32), ("primary_pass", C.c_uint32),
-        ("batch_stride", C.c_uint32), ("first_batch", C.c_uint32), ("tail_bounce", C.c_uint32), ("reserved", C.c_uint32 * 1),
+        ("batch_stride", C.c_uint32), ("first_batch", C.c_uint32), ("tail_bounce", C.c_uint32), ("chunk_overlap", C.c_uint32),
     ]
 
 

@@ -128,6 +128,11 @@ struct b200rt_scene {
   StreamPipe pipe;
   std::vector<cudaEvent_t> timerEvents;                // pool of the per-kernel timing events (KernelTimer), kept across calls
   DeviceBuffer slotColor, slotEscape, slotEnv, escapeQueue, escapeCount;  // NIF wavefront
+  // Chunk overlap (render_tile): the NIF + accumulate of chunk c run on nifStream while sc.stream traces chunk c + 1
+  // into the second set of per-sample records.
+  DeviceBuffer slotColorB, slotEscapeB, escapeQueueB, escapeCountB;
+  cudaStream_t nifStream = nullptr;
+  cudaEvent_t evTraceDone[2]{}, evNifDone[2]{};
   DeviceBuffer wfState[2][7], wfHitA, wfHitB, wfCounts;  // wavefront path state (two slot-indexed arrays of records)
   b200rt_trace_stats stats{};
   float hdriRotationDegrees = 0.f;
@@ -140,8 +145,11 @@ struct b200rt_scene {
     if (nif) rt::nif_destroy(nif);
     for (DeviceBuffer* b : {&nodes, &pairs, &leafOrig, &leafInfo, &geoms, &triVerts, &triNormals, &triFaceNormals, &spheres, &discs, &matIDs, &materials,
                             &workCounter, &counters, &primA, &primB, &rays, &slotColor, &slotEscape, &slotEnv, &escapeQueue,
-                            &escapeCount, &wfHitA, &wfHitB, &wfCounts})
+                            &escapeCount, &wfHitA, &wfHitB, &wfCounts, &slotColorB, &slotEscapeB, &escapeQueueB, &escapeCountB})
       b->release();
+    for (cudaEvent_t e : {evTraceDone[0], evTraceDone[1], evNifDone[0], evNifDone[1]})
+      if (e) cudaEventDestroy(e);
+    if (nifStream) cudaStreamDestroy(nifStream);
     for (auto& set : wfState)
       for (DeviceBuffer& b : set) b.release();
     pipe.release();
@@ -272,6 +280,12 @@ cudaError_t run_path(b200rt_scene& sc, const LaunchPlan& L, bool nif, const rt::
                    : dispatch_path<false, false>(L.count, nif, a, L.grid, L.block, L.smem, sc.stream);
 }
 
+// Default of b200rt_trace_params::chunk_overlap = 0 (see render_tile); build knob for A/B runs.
+#ifndef B200RT_CHUNK_OVERLAP_DEFAULT
+#define B200RT_CHUNK_OVERLAP_DEFAULT 1
+#endif
+constexpr bool kChunkOverlapDefault = B200RT_CHUNK_OVERLAP_DEFAULT != 0;
+
 // Per-kernel device timing with CUDA event pairs recorded on the launching stream.
 struct KernelTimer {
   enum Kind { TRACE = 0, NIF = 1, ACCUM = 2, SHADE = 3 };
@@ -331,7 +345,7 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
   // traversal 3 (the state-machine megakernel of round 1, measured slower) is gone: it selects the wavefront tracer too.
   const bool wavefront = sc.desc.path_trace && (p.traversal == 4 || p.traversal == 3 ||
                                                (p.traversal == 0 && sc.desc.max_path_length <= 255));
-  const LaunchPlan L = plan_launch(sc, p, wavefront);
+  LaunchPlan L = plan_launch(sc, p, wavefront);
   rt::TraceArgs a{};
   a.scene = sc.dev;
   a.rays = d_rays;
@@ -443,11 +457,55 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
         w.b.counts = (uint32_t*)sc.wfCounts.p;
         w.lastSample = first + count - 1;
       }
-      for (uint32_t s0 = first; s0 < first + count; s0 += chunk) {
+      // Chunk overlap: the NIF MLP (tensor pipe, weights streamed from L2) and the accumulate of chunk c run on a second
+      // stream while sc.stream traces and shades chunk c + 1 (issue- and HBM-bound SIMT work) into the other set of
+      // per-sample records; the accumulates stay in chunk order on that one stream, so rgb is bit-identical.
+      // params.chunk_overlap: 0 = auto, 1 = off, 2 = on; B200RT_OVERLAP=0/1 overrides it for A/B runs.
+      static const int envOverlap = [] { const char* e = std::getenv("B200RT_OVERLAP"); return e ? std::atoi(e) : -1; }();
+      const bool overlapWanted = envOverlap >= 0 ? envOverlap != 0 : (p.chunk_overlap == 0u ? kChunkOverlapDefault : p.chunk_overlap == 2u);
+      const bool overlap = overlapWanted && sc.nif && wavefront && count > chunk;
+      if (overlap) {
+        if (!sc.nifStream) {
+          // higher priority than sc.stream: when an SM frees resources the NIF's one CTA per SM is placed before the
+          // next trace / shade blocks, which then fill what is left beside it
+          static const bool envPrio = [] { const char* e = std::getenv("B200RT_NIF_PRIORITY"); return !e || e[0] != '0'; }();
+          int prioLow = 0, prioHigh = 0;
+          CU_TRY(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+          CU_TRY(cudaStreamCreateWithPriority(&sc.nifStream, cudaStreamNonBlocking, envPrio ? prioHigh : prioLow));
+          for (int k = 0; k < 2; ++k) {
+            CU_TRY(cudaEventCreateWithFlags(&sc.evTraceDone[k], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&sc.evNifDone[k], cudaEventDisableTiming));
+          }
+        }
+        CU_TRY(sc.slotColorB.reserve(P * 3 * sizeof(float)));
+        CU_TRY(sc.slotEscapeB.reserve(P * 5 * sizeof(float)));
+        CU_TRY(sc.escapeQueueB.reserve(P * sizeof(uint32_t)));
+        CU_TRY(sc.escapeCountB.reserve(16));
+      }
+      if (overlap && L.shared && p.scene_residency == 0u) {
+        // The NIF CTA fills its SM's shared memory, so a wf_trace CTA that stages the pair table could only alternate with
+        // it. The L2-resident form (128-thread CTAs, table read through L1; 2 % slower alone) runs beside it.
+        b200rt_trace_params pl2 = p;
+        pl2.scene_residency = 2u;
+        L = plan_launch(sc, pl2, wavefront);
+      }
+      cudaStream_t const nifStream = overlap ? sc.nifStream : sc.stream;
+      uint32_t chunkIndex = 0;
+      for (uint32_t s0 = first; s0 < first + count; s0 += chunk, ++chunkIndex) {
         const uint32_t c = std::min(chunk, first + count - s0);
         a.firstSample = s0;
         a.endSample = s0 + c;
-        CU_TRY(cudaMemsetAsync(sc.escapeCount.p, 0, 4, sc.stream));
+        const int set = overlap ? (int)(chunkIndex & 1u) : 0;
+        if (set) {
+          a.slotColor = (float*)sc.slotColorB.p; a.slotEscape = (float*)sc.slotEscapeB.p;
+          a.escapeQueue = (uint32_t*)sc.escapeQueueB.p; a.escapeCount = (uint32_t*)sc.escapeCountB.p;
+        } else if (slots) {
+          a.slotColor = (float*)sc.slotColor.p; a.slotEscape = (float*)sc.slotEscape.p;
+          a.escapeQueue = (uint32_t*)sc.escapeQueue.p; a.escapeCount = (uint32_t*)sc.escapeCount.p;
+        }
+        // this set's records are free again once the NIF + accumulate of two chunks ago are done
+        if (overlap && chunkIndex >= 2u) CU_TRY(cudaStreamWaitEvent(sc.stream, sc.evNifDone[set], 0));
+        CU_TRY(cudaMemsetAsync(set ? sc.escapeCountB.p : sc.escapeCount.p, 0, 4, sc.stream));
         if (!wavefront) {
           CU_TRY(cudaMemsetAsync(sc.workCounter.p, 0, 8, sc.stream));
           timer.begin(KernelTimer::TRACE, sc.stream);  // one span: pre-pass + path tracer = the trace step of a chunk
@@ -542,27 +600,33 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
             }
           }
         }
+        if (overlap) {
+          CU_TRY(cudaEventRecord(sc.evTraceDone[set], sc.stream));
+          CU_TRY(cudaStreamWaitEvent(nifStream, sc.evTraceDone[set], 0));
+        }
         if (sc.nif) {
           int nifLaunches = 0;
-          timer.begin(KernelTimer::NIF, sc.stream);
-          const int rc = rt::nif_eval_queue(sc.nif, (const float*)sc.slotEscape.p, (const uint32_t*)sc.escapeQueue.p,
-                                            (const uint32_t*)sc.escapeCount.p, (uint32_t)std::min<size_t>((size_t)c * n, 0xFFFFFFFFull),
-                                            (uint32_t)std::min<size_t>(sc.maxNifBatch, 0xFFFFFFFFull), (float*)sc.slotEnv.p, sc.stream,
+          timer.begin(KernelTimer::NIF, nifStream);
+          const int rc = rt::nif_eval_queue(sc.nif, a.slotEscape, a.escapeQueue, a.escapeCount,
+                                            (uint32_t)std::min<size_t>((size_t)c * n, 0xFFFFFFFFull),
+                                            (uint32_t)std::min<size_t>(sc.maxNifBatch, 0xFFFFFFFFull), (float*)sc.slotEnv.p, nifStream,
                                             &nifLaunches);
-          timer.end(sc.stream, nifLaunches);
+          timer.end(nifStream, nifLaunches);
           if (rc != 0) return fail(B200RT_ERR_CUDA, std::string("NIF evaluation failed: ") + rt::nif_last_error());
           launches += (uint64_t)nifLaunches;
         }
         if (!slots) continue;  // path tracer without an environment light: rgb was accumulated in the kernel
         const uint32_t threads = 256, blocks = (uint32_t)((n + rt::kAccPixels - 1) / rt::kAccPixels);
-        timer.begin(KernelTimer::ACCUM, sc.stream);
-        rt::wf_accumulate_kernel<<<blocks, threads, 0, sc.stream>>>(d_rays, (uint32_t)n, c, (const float*)sc.slotColor.p,
-                                                                    (const float*)sc.slotEscape.p,
+        timer.begin(KernelTimer::ACCUM, nifStream);
+        rt::wf_accumulate_kernel<<<blocks, threads, 0, nifStream>>>(d_rays, (uint32_t)n, c, a.slotColor, a.slotEscape,
                                                                     sc.nif ? (const float*)sc.slotEnv.p : nullptr);
-        timer.end(sc.stream);
+        timer.end(nifStream);
         CU_TRY(cudaGetLastError());
         launches += 1;
+        if (overlap) CU_TRY(cudaEventRecord(sc.evNifDone[set], nifStream));
       }
+      // join: whatever follows on sc.stream (the next tile, the D2H copy, evStop) is ordered after the last accumulate
+      if (overlap && chunkIndex > 0u) CU_TRY(cudaStreamWaitEvent(sc.stream, sc.evNifDone[(chunkIndex - 1u) & 1u], 0));
     }
   }
   return B200RT_OK;

@@ -44,7 +44,10 @@ namespace tc {
 
 constexpr int kRows = 128;          // rows (escaped rays) per tile == TMEM lanes
 constexpr int kHalfN = 160;         // output columns per MMA instruction / per accumulator slot
-constexpr int kStages = 6;          // weight ring depth
+#ifndef B200RT_NIF_STAGES
+#define B200RT_NIF_STAGES 6
+#endif
+constexpr int kStages = B200RT_NIF_STAGES;  // weight ring depth
 constexpr int kStageK = 64;         // K elements per ring stage (4 MMA K-slices of one block)
 constexpr int kMaxLayers = 16;
 constexpr int kEpiWarps = 8;

@@ -44,7 +44,7 @@ struct WfBuffers {
   WfState st[2];
   float2* hitA;      // [slot] closest t, leaf reference of the winner (kRefNone = no hit)
   float4* hitB;      // [slot] b0, b1, b2; only when the scene interpolates normals (else null)
-  uint32_t* counts;  // [0], [1]: live paths in st[0] / st[1]; [2]: fetch cursor of wf_trace
+  uint32_t* counts;  // [0], [1]: live paths in st[0] / st[1]; [2]: fetch cursor of wf_trace; [3]: round cursor of wf_shade
 };
 
 struct WfArgs {
@@ -135,7 +135,8 @@ __device__ __forceinline__ void wf_trace_body(const WfArgs& a, const int qIn, co
   const uint32_t count = kFirst ? a.numPaths : __ldcg(a.b.counts + qIn);
   uint32_t* cursor = a.b.counts + 2;
   // the shading kernel that follows appends its survivors to the other array: empty it (nobody reads that counter here)
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[qIn ^ 1] = 0u;
+  // ... and that kernel claims its rounds from slot 0 again
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.b.counts[qIn ^ 1] = 0u; a.b.counts[3] = 0u; }
   Counters cnt = {0u, 0u};
   unsigned nClosest = 0;
   constexpr int kTravThreshold = kFirst ? B200RT_TRAV_THRESHOLD_FIRST : B200RT_TRAV_THRESHOLD;
@@ -295,7 +296,8 @@ constexpr int kShadeBlocksPerSM = B200RT_SHADE_BLOCKS * (256 / kShadeThreads);
 // The kernel's body for blocks of kWarps warps (2, 4 or 8: wf_shade_kernel; 32: wf_tail_kernel). sCountBuf is the
 // block's [round parity][queue][warp] scratch: the next round posts into the other half.
 template <bool kNif, bool kFirst, int kWarps>
-__device__ __forceinline__ void wf_shade_body(const WfArgs& a, const int qIn, uint32_t (*sCountBuf)[2][kWarps < 8 ? 8 : kWarps]) {
+__device__ __forceinline__ void wf_shade_body(const WfArgs& a, const int qIn, uint32_t (*sCountBuf)[2][kWarps < 8 ? 8 : kWarps],
+                                              uint32_t* sClaim) {
   const TraceArgs& t = a.t;
   const DevScene& sc = t.scene;
   const unsigned lane = threadIdx.x & 31, full = 0xffffffffu;
@@ -307,18 +309,26 @@ __device__ __forceinline__ void wf_shade_body(const WfArgs& a, const int qIn, ui
   if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[2] = 0u;
   unsigned nSamples = 0, nEscaped = 0;
   static_assert(kWarps == 32 || kWarps == 8 || kWarps == 4 || kWarps == 2, "block-level append: 2, 4, 8 or 32 warps");
-  // whole blocks iterate together (uniform trip count) so the ballots and barriers below see converged threads
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t rounds = (count + stride - 1) / stride;
-  for (uint32_t r = 0; r < rounds; ++r) {
+  // Whole blocks iterate together (uniform trip count) so the ballots and barriers below see converged threads. A round
+  // is blockDim.x consecutive slots claimed from a grid-wide cursor (counts[3]): blocks that run beside another kernel's
+  // CTA on their SM (chunk overlap: the NIF kernel of the previous chunk), or start late because of it, simply claim
+  // fewer rounds. Claims run two rounds ahead (sClaim is a ring of 4) so that the next round's slots are known at the top
+  // of this one for the L2 prefetch; a claim is published by the round's first barrier and read after its second.
+  uint32_t* const roundCursor = a.b.counts + 3;
+  if (threadIdx.x == 0) { sClaim[0] = atomicAdd(roundCursor, blockDim.x); sClaim[1] = atomicAdd(roundCursor, blockDim.x); }
+  __syncthreads();
+  uint32_t cur = sClaim[0], nxt = sClaim[1];
+  for (uint32_t r = 0; cur < count; ++r) {
     uint32_t (*sCount)[kWarps < 8 ? 8 : kWarps] = sCountBuf[r & 1u];
-    const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) sClaim[(r + 2u) & 3u] = nxt < count ? atomicAdd(roundCursor, blockDim.x) : 0xFFFFFFFFu;
+    const uint32_t i = cur + threadIdx.x;
     const bool valid = i < count;
 #if B200RT_SHADE_PREFETCH
     // the records of the block's next round are on their way from DRAM to L2 while this round is shaded
-    if (i + stride < count) {
-      prefetch_l2(a.b.hitA + i + stride);
-      if (!kFirst) { prefetch_l2(in.rayO + i + stride); prefetch_l2(in.rayD + i + stride); prefetch_l2(in.thr + i + stride); prefetch_l2(in.rng + i + stride); }
+    if (nxt < count && nxt + threadIdx.x < count) {
+      const uint32_t in2 = nxt + threadIdx.x;
+      prefetch_l2(a.b.hitA + in2);
+      if (!kFirst) { prefetch_l2(in.rayO + in2); prefetch_l2(in.rayD + in2); prefetch_l2(in.thr + in2); prefetch_l2(in.rng + in2); }
     }
 #endif
     bool survive = false, lastOne = false;
@@ -496,6 +506,8 @@ __device__ __forceinline__ void wf_shade_body(const WfArgs& a, const int qIn, ui
       // no third barrier: the next round posts its counts into the other half of sCountBuf, and a warp can only get
       // two rounds ahead of another by passing that round's first barrier, which every warp must reach
     }
+    cur = nxt;
+    nxt = sClaim[(r + 2u) & 3u];
   }
   flush_counters(t.counters, 0u, 0u, Counters{0u, 0u}, nSamples, nEscaped);
 }
@@ -503,7 +515,8 @@ __device__ __forceinline__ void wf_shade_body(const WfArgs& a, const int qIn, ui
 template <bool kNif, bool kFirst>
 __global__ void __launch_bounds__(kShadeThreads, kShadeBlocksPerSM) wf_shade_kernel(const WfArgs a) {
   __shared__ uint32_t sCountBuf[2][2][8];
-  wf_shade_body<kNif, kFirst, kShadeWarps>(a, a.qIn, sCountBuf);
+  __shared__ uint32_t sClaim[4];
+  wf_shade_body<kNif, kFirst, kShadeWarps>(a, a.qIn, sCountBuf, sClaim);
 }
 
 // wf_tail: the bounces from `bounceBegin` on in ONE cooperative launch (persistent 1024-thread CTAs, one per SM, the pair
@@ -518,6 +531,7 @@ template <bool kShared, bool kCount, bool kNif>
 __global__ void __launch_bounds__(1024) wf_tail_kernel(const WfArgs a, const uint32_t bounceBegin, const uint32_t bounceEnd) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ uint32_t sCountBuf[2][2][32];
+  __shared__ uint32_t sClaim[4];
   const uint4* pairs = stage_pairs<kShared>(a.t, reinterpret_cast<uint4*>(smemRaw));
   const uint32_t pairsShared = opaque_shared_base<kShared>(smemRaw);
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
@@ -525,7 +539,7 @@ __global__ void __launch_bounds__(1024) wf_tail_kernel(const WfArgs a, const uin
     const int qIn = (int)(b & 1u);
     wf_trace_body<kShared, kCount, false>(a, qIn, pairs, pairsShared, nullptr);
     grid.sync();
-    wf_shade_body<kNif, false, 32>(a, qIn, sCountBuf);
+    wf_shade_body<kNif, false, 32>(a, qIn, sCountBuf, sClaim);
     grid.sync();
     if (__ldcg(a.b.counts + (qIn ^ 1)) == 0u) break;  // nobody survived this bounce (every thread reads the same value)
   }

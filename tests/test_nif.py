@@ -185,3 +185,37 @@ def test_config2_nif_lit_window_of_the_full_frame(port):
     assert np.abs(got["rgb"].astype(np.float64) - want["rgb"]).sum() / np.abs(want["rgb"]).sum() < MEAN_REL
     rel = np.abs(got["rgb"] - want["rgb"]).max(axis=1) / np.maximum(np.abs(want["rgb"]).max(axis=1), 1e-6)
     assert np.mean(rel > MAX_REL) < 5e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h,spp,chunk,residency", [("box", 96, 80, 13, 2, 0), ("spheres", 80, 64, 9, 1, 0),
+                                                        ("box", 200, 120, 12, 4, 1), ("box", 64, 48, 5, 8, 0)])
+def test_chunk_overlap_is_bit_identical(name, w, h, spp, chunk, residency):
+    """b200rt_trace_params.chunk_overlap: the NIF + accumulate of chunk c on a second stream beside the trace / shade
+    kernels of chunk c + 1 (two sets of per-sample records, accumulates in chunk order) leaves the same bytes in the
+    stream as the serialised chunks -- every field, rgb included -- for many small chunks, an odd chunk count, a single
+    chunk (nothing to overlap), an explicit shared-memory residency and serial NIF micro-batches."""
+    from ipu_ray_lib_b200.render import B200Scene
+    s = scene.HostScene.builtin(name).configure(w, h, path_trace=True, samples=spp, seed=77)
+    nif = NifWeights.synthetic(seed=1442)
+    base = scene.init_ray_stream(w, h, s.fov)
+    with B200Scene(s) as g:
+        g.load_nif_model(nif)
+        g.set_hdri_rotation(35.0)
+        serial = base.copy()
+        g.execute(serial, samples_per_chunk=chunk, chunk_overlap=1, scene_residency=residency)
+        launches = g.stats()["kernel_launches"]
+        for mode in (2, 0):  # on, auto
+            got = base.copy()
+            g.execute(got, samples_per_chunk=chunk, chunk_overlap=mode, scene_residency=residency)
+            assert got.tobytes() == serial.tobytes(), f"chunk_overlap={mode}"
+            assert g.stats()["kernel_launches"] == launches
+        g.set_max_nif_batch_size(500)
+        got = base.copy()
+        g.execute(got, samples_per_chunk=chunk, chunk_overlap=2, scene_residency=residency)
+        assert got.tobytes() == serial.tobytes(), "chunk_overlap with NIF micro-batches"
+        # sample ranges compose across calls with the overlap on
+        half = base.copy()
+        g.execute(half, samples_per_chunk=chunk, chunk_overlap=2, first_sample=0, num_samples=spp // 2)
+        g.execute(half, samples_per_chunk=chunk, chunk_overlap=2, first_sample=spp // 2, num_samples=spp - spp // 2)
+        assert half["rgb"].tobytes() == serial["rgb"].tobytes()
