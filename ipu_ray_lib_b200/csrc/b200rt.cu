@@ -420,6 +420,17 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
       const size_t budget = envBudget ? envBudget << 30 : (wavefront ? (size_t)24 << 30 : (size_t)8 << 30);
       while (chunk > 1 && (size_t)chunk * n * perSlot > budget) chunk /= 2;
       if (chunk > count) chunk = count ? count : 1;
+      // Chunk overlap (below) needs at least two chunks: a short render that would fit one chunk is cut into up to four,
+      // as long as a chunk keeps >= 4 M paths (kernels of that size still run at full rate: 8-spp chunks of the 1440^2
+      // frame cost 2.5 % over 32-spp ones, profiles/r02_overlap_ab.txt).
+      static const int envOverlap = [] { const char* e = std::getenv("B200RT_OVERLAP"); return e ? std::atoi(e) : -1; }();
+      const bool overlapWanted = (envOverlap >= 0 ? envOverlap != 0 : (p.chunk_overlap == 0u ? kChunkOverlapDefault : p.chunk_overlap == 2u)) &&
+                                 sc.nif && wavefront;
+      if (overlapWanted && !p.samples_per_chunk && chunk >= count && count >= 2u) {
+        uint32_t parts = 4u;
+        while (parts > 1u && (size_t)((count + parts - 1u) / parts) * n < ((size_t)4 << 20)) --parts;
+        chunk = (count + parts - 1u) / parts;
+      }
       if ((size_t)chunk * n > 0xFFFFFFF0ull) return fail(B200RT_ERR_UNSUPPORTED, "ray stream too long for one chunk");
       const size_t P = (size_t)chunk * n;
       CU_TRY(sc.escapeCount.reserve(16));
@@ -461,9 +472,7 @@ int render_tile(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays, s
       // stream while sc.stream traces and shades chunk c + 1 (issue- and HBM-bound SIMT work) into the other set of
       // per-sample records; the accumulates stay in chunk order on that one stream, so rgb is bit-identical.
       // params.chunk_overlap: 0 = auto, 1 = off, 2 = on; B200RT_OVERLAP=0/1 overrides it for A/B runs.
-      static const int envOverlap = [] { const char* e = std::getenv("B200RT_OVERLAP"); return e ? std::atoi(e) : -1; }();
-      const bool overlapWanted = envOverlap >= 0 ? envOverlap != 0 : (p.chunk_overlap == 0u ? kChunkOverlapDefault : p.chunk_overlap == 2u);
-      const bool overlap = overlapWanted && sc.nif && wavefront && count > chunk;
+      const bool overlap = overlapWanted && count > chunk;
       if (overlap) {
         if (!sc.nifStream) {
           // higher priority than sc.stream: when an SM frees resources the NIF's one CTA per SM is placed before the

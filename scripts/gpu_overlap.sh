@@ -7,15 +7,11 @@ while read -r label lib envs; do
   [ -z "$label" ] && continue
   echo -n "$label: "; env $envs B200RT_LIB=$PWD/ipu_ray_lib_b200/$lib timeout 300 python scripts/overlap_times.py $SPP 3 2>&1 | tail -2 | tr '\n' ' '; echo
 done <<'CASES'
-base libb200rt.so
-ov_l2 libb200rt.so WF_CHUNK_OVERLAP=2 WF_SCENE_RESIDENCY=2 WF_CHECK=1
-ov_l2_g136 libb200rt.so WF_CHUNK_OVERLAP=2 WF_SCENE_RESIDENCY=2 B200RT_NIF_GRID=136
-ov_l2_g128 libb200rt.so WF_CHUNK_OVERLAP=2 WF_SCENE_RESIDENCY=2 B200RT_NIF_GRID=128
-ov_l2_g120 libb200rt.so WF_CHUNK_OVERLAP=2 WF_SCENE_RESIDENCY=2 B200RT_NIF_GRID=120
-ov_l2_g112 libb200rt.so WF_CHUNK_OVERLAP=2 WF_SCENE_RESIDENCY=2 B200RT_NIF_GRID=112
-ov_l2_g100 libb200rt.so WF_CHUNK_OVERLAP=2 WF_SCENE_RESIDENCY=2 B200RT_NIF_GRID=100
-ov_sh_g120 libb200rt.so WF_CHUNK_OVERLAP=2 B200RT_NIF_GRID=120
-ov_sh_g100 libb200rt.so WF_CHUNK_OVERLAP=2 B200RT_NIF_GRID=100
-base2 libb200rt.so
+ov_auto libb200rt.so
+ov_c16 libb200rt.so WF_SAMPLES_PER_CHUNK=16
+ov_c8 libb200rt.so WF_SAMPLES_PER_CHUNK=8
+ov_c64 libb200rt.so WF_SAMPLES_PER_CHUNK=64
+serial_c16 libb200rt.so WF_SAMPLES_PER_CHUNK=16 WF_CHUNK_OVERLAP=1
+serial libb200rt.so WF_CHUNK_OVERLAP=1
 CASES
 nvidia-smi --query-gpu=clocks.sm,power.draw --format=csv,noheader

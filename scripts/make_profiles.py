@@ -50,7 +50,7 @@ for l in launch.values():
 total = sum(a["ms"] for a in agg.values())
 shutil.copy(src / f"{tag}_launches.csv", out / f"{tag}_launches.csv")
 with open(out / f"{tag}_launches_summary.txt", "w") as f:
-    f.write(f"# ncu launch list of `python bench.py --steps 1 --warmup 0 --samples {int(spp_list)} --skip-cpu-baseline` ({len(launch)} launches captured: bounce-0 to bounce-4 "
+    f.write(f"# ncu launch list of `python bench.py --steps 1 --warmup 0 --samples {int(spp_list)} --skip-cpu-baseline` with B200RT_OVERLAP=0 (chunks serialised, like bench.py's roofline step; {len(launch)} launches captured: bounce-0 to bounce-4 "
             f"trace / shade pairs, the tail launch, NIF and accumulate of each 32-spp chunk), --clock-control none; per-launch times under ncu are serialised and cold-cache:\n"
             f"# the SHARES are what must agree with bench.py's event timing, not the absolute times.\n"
             f"# kernel, launches, total ms, share, avg ms, DRAM read GB, DRAM write GB, lanes per instruction (time-weighted), issue-active % (time-weighted)\n")
