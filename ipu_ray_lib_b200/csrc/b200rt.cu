@@ -681,7 +681,12 @@ int render_device(b200rt_scene& sc, const b200rt_trace_params& p, float* d_rays,
   struct Restore { b200rt_scene& s; cudaStream_t v; ~Restore() { s.stream = v; } } restore{sc, saved};
   RenderRun run(sc);
   if (int rc = render_begin(sc, run)) return rc;
-  if (int rc = render_enqueue(sc, p, d_rays, n, run)) return rc;
+  if (int rc = render_enqueue(sc, p, d_rays, n, run)) {
+    // nothing of a failed render may still be running when the caller frees or reuses its buffers
+    cudaStreamSynchronize(sc.stream);
+    if (sc.nifStream) cudaStreamSynchronize(sc.nifStream);
+    return rc;
+  }
   return render_end(sc, run);
 }
 
@@ -930,7 +935,7 @@ int b200rt_trace(b200rt_scene* sc, const b200rt_trace_params* params, void* rays
   // an early error return must not leave copies, kernels or queued callbacks (which point into `jobs`) in flight
   struct Drain {
     b200rt_scene& s; bool armed = true;
-    ~Drain() { if (armed) { cudaStreamSynchronize(s.pipe.in); cudaStreamSynchronize(s.stream); cudaStreamSynchronize(s.pipe.out); } }
+    ~Drain() { if (armed) { cudaStreamSynchronize(s.pipe.in); cudaStreamSynchronize(s.stream); if (s.nifStream) cudaStreamSynchronize(s.nifStream); cudaStreamSynchronize(s.pipe.out); } }
   } drain{*sc};
   if (int rc = render_begin(*sc, run)) return rc;
   for (size_t k = 0; k < numTiles; ++k) {

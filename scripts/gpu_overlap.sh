@@ -7,11 +7,11 @@ while read -r label lib envs; do
   [ -z "$label" ] && continue
   echo -n "$label: "; env $envs B200RT_LIB=$PWD/ipu_ray_lib_b200/$lib timeout 300 python scripts/overlap_times.py $SPP 3 2>&1 | tail -2 | tr '\n' ' '; echo
 done <<'CASES'
-ov_auto libb200rt.so
-ov_c16 libb200rt.so WF_SAMPLES_PER_CHUNK=16
-ov_c8 libb200rt.so WF_SAMPLES_PER_CHUNK=8
-ov_c64 libb200rt.so WF_SAMPLES_PER_CHUNK=64
-serial_c16 libb200rt.so WF_SAMPLES_PER_CHUNK=16 WF_CHUNK_OVERLAP=1
+ov libb200rt.so
+ov_sb8 variants/libb200rt_sb8.so
+serial_sb8 variants/libb200rt_sb8.so WF_CHUNK_OVERLAP=1
 serial libb200rt.so WF_CHUNK_OVERLAP=1
+ov2 libb200rt.so
+ov_sb8_2 variants/libb200rt_sb8.so
 CASES
 nvidia-smi --query-gpu=clocks.sm,power.draw --format=csv,noheader
