@@ -130,7 +130,9 @@ typedef struct b200rt_trace_stats {
   double   trace_secs;            /* wall time; same span as IpuScene::getTraceTimeSecs (src/IpuScene.cpp:672-696) */
   uint64_t kernel_launches;       /* number of kernels this library launched */
   double   trace_kernel_ms;       /* sum over launches of shadow_trace / path_trace / wf_trace kernel time (CUDA events) */
-  double   nif_kernel_ms;         /* sum over launches of the NIF MLP kernel time */
+  double   nif_kernel_ms;         /* sum over launches of the NIF MLP kernel time. With chunk_overlap on, the NIF of one
+                                   * chunk shares the SMs with the trace / shade kernels of the next: the per-kernel sums
+                                   * are event spans that include that sharing and add up to more than kernel_ms */
   double   accumulate_kernel_ms;  /* sum over launches of the ordered rgb accumulation kernel */
   uint64_t trace_kernel_launches, nif_kernel_launches;
   double   shade_kernel_ms;       /* wavefront path tracer: sum over launches of the shade kernels */
