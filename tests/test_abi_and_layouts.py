@@ -59,6 +59,30 @@ def test_c_struct_sizes():
     assert C.sizeof(capi.SceneDesc) % 8 == 0
 
 
+def test_ctypes_mirrors_follow_the_header_field_by_field():
+    """The ctypes structures name the same fields in the same order as include/b200rt.h (a renamed or inserted field
+    in one of them would otherwise pass the size checks)."""
+    import re
+    from pathlib import Path
+    hdr = (Path(__file__).resolve().parents[1] / "include" / "b200rt.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+
+    def header_fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:  # "type a, b" declares two fields
+                first, *rest = decl.split(",")
+                for d in [first.split()[-1]] + [r.strip() for r in rest]:
+                    out.append(re.sub(r"\[.*", "", d.lstrip("*")))
+        return out
+
+    for cname, mirror in (("b200rt_trace_params", capi.TraceParams), ("b200rt_trace_stats", capi.TraceStats),
+                          ("b200rt_scene_desc", capi.SceneDesc)):
+        assert header_fields(cname) == [f for f, _ in mirror._fields_], cname
+
+
 def test_bad_arguments_are_rejected_with_a_message(box_scene):
     lib = capi.lib()
     out = C.c_void_p()
