@@ -272,8 +272,13 @@ __device__ __forceinline__ uint32_t opaque_shared_base(const void* smemRaw) {
   return base;
 }
 
+// The L2-resident form is launched as 128-thread CTAs, eight per SM at 64 registers (B200RT_WF_L2_MINBLOCKS: A/B knob for
+// leaner CTAs beside the NIF kernel).
+#ifndef B200RT_WF_L2_MINBLOCKS
+#define B200RT_WF_L2_MINBLOCKS 8
+#endif
 template <bool kShared, bool kCount, bool kFirst>
-__global__ void __launch_bounds__(1024) wf_trace_kernel(const WfArgs a) {
+__global__ void __launch_bounds__(kShared ? 1024 : 128, kShared ? 1 : B200RT_WF_L2_MINBLOCKS) wf_trace_kernel(const WfArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const uint4* pairs = stage_pairs<kShared>(a.t, reinterpret_cast<uint4*>(smemRaw));
   wf_trace_body<kShared, kCount, kFirst>(a, a.qIn, pairs, opaque_shared_base<kShared>(smemRaw), a.phaseStats);
