@@ -44,6 +44,11 @@ namespace tc {
 
 constexpr int kRows = 128;          // rows (escaped rays) per tile == TMEM lanes
 constexpr int kHalfN = 160;         // output columns per MMA instruction / per accumulator slot
+// A/B knob: __launch_bounds__ minimum blocks per SM of the kernel = its register cap (1: 96 registers as compiled;
+// 3: 64). Fewer registers would leave more warps of the bounce kernels beside the CTA under the chunk overlap.
+#ifndef B200RT_NIF_MINBLOCKS
+#define B200RT_NIF_MINBLOCKS 1
+#endif
 #ifndef B200RT_NIF_STAGES
 #define B200RT_NIF_STAGES 6
 #endif
@@ -257,7 +262,7 @@ __device__ __forceinline__ void drain_to_regs(uint32_t taddr, bool relu, uint32_
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, B200RT_NIF_MINBLOCKS)
 nif_mlp_tc_kernel(const Params p, const float* __restrict__ uvDirect, const float* __restrict__ slotEscape,
                   const uint32_t* __restrict__ queue, const uint32_t* __restrict__ dCount, uint32_t directCount,
                   uint32_t first, float* __restrict__ out) {
