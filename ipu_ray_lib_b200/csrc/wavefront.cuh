@@ -111,6 +111,18 @@ enum : uint32_t { WF_TRAV = 0, WF_LEAF = 1, WF_FETCH = 2 };
 #define WF_LD(p) (*(p))
 #define WF_ST(p, v) (*(p) = (v))
 #endif
+// wf_trace: path records read and hits written with streaming (evict-first) hints, so that they do not displace the pair
+// table and the traversal stacks from L1 (matters for the L2-resident form). A/B knob.
+#ifndef B200RT_TRACE_STREAMING_HINTS
+#define B200RT_TRACE_STREAMING_HINTS 0
+#endif
+#if B200RT_TRACE_STREAMING_HINTS
+#define WFT_LD(p) __ldcs(p)
+#define WFT_ST(p, v) __stcs(p, v)
+#else
+#define WFT_LD(p) (*(p))
+#define WFT_ST(p, v) (*(p) = (v))
+#endif
 #ifndef B200RT_SHADE_BLOCKS
 #define B200RT_SHADE_BLOCKS 6
 #endif
@@ -226,8 +238,8 @@ __device__ __forceinline__ void wf_trace_body(const WfArgs& a, const int qIn, co
       if (served) {
         if (slot != 0xFFFFFFFFu) {
           // the shading kernel turns the winner's leaf reference into geomID / primID (stream_hit_ids)
-          a.b.hitA[slot] = make_float2(q.hitT, __uint_as_float(q.hitRef));
-          if (a.b.hitB) a.b.hitB[slot] = make_float4(q.b0, q.b1, q.b2, 0.f);
+          WFT_ST(a.b.hitA + slot, make_float2(q.hitT, __uint_as_float(q.hitRef)));
+          if (a.b.hitB) WFT_ST(a.b.hitB + slot, make_float4(q.b0, q.b1, q.b2, 0.f));
           slot = 0xFFFFFFFFu;
         }
         if (qi >= count) {
@@ -245,7 +257,7 @@ __device__ __forceinline__ void wf_trace_body(const WfArgs& a, const int qIn, co
             stream_begin(sc, q, o, d);
           } else {
             // bounce rays come with their constants (the shading kernel made them: stream_prepare)
-            const float4 ro = in.rayO[slot], ri = in.rayI[slot], rs = in.rayS[slot];
+            const float4 ro = WFT_LD(in.rayO + slot), ri = WFT_LD(in.rayI + slot), rs = WFT_LD(in.rayS + slot);
             stream_begin_prepared(sc, q, mk(ro.x, ro.y, ro.z), mk(ri.x, ri.y, ri.z), rs.x, rs.y, rs.z, __float_as_uint(rs.w));
           }
           // the handful of queries in which a NaN could occur (a zero in the direction, coordinates beyond 2^20) take

@@ -8,10 +8,10 @@ while read -r label lib envs; do
   echo -n "$label: "; env $envs B200RT_LIB=$PWD/ipu_ray_lib_b200/$lib timeout 300 python scripts/overlap_times.py $SPP 3 2>&1 | tail -2 | tr '\n' ' '; echo
 done <<'CASES'
 ov libb200rt.so
-ov_mb2 variants/libb200rt_mb2.so
-ov_mb3 variants/libb200rt_mb3.so
+ov_tsh variants/libb200rt_tsh.so
+l2_serial libb200rt.so WF_CHUNK_OVERLAP=1 WF_SCENE_RESIDENCY=2
+l2_serial_tsh variants/libb200rt_tsh.so WF_CHUNK_OVERLAP=1 WF_SCENE_RESIDENCY=2
 serial libb200rt.so WF_CHUNK_OVERLAP=1
-serial_mb2 variants/libb200rt_mb2.so WF_CHUNK_OVERLAP=1
-serial_mb3 variants/libb200rt_mb3.so WF_CHUNK_OVERLAP=1
+serial_tsh variants/libb200rt_tsh.so WF_CHUNK_OVERLAP=1
 CASES
 nvidia-smi --query-gpu=clocks.sm,power.draw --format=csv,noheader
